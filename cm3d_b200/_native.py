@@ -1,0 +1,72 @@
+"""ctypes binding of the C-ABI library (include/cm3d_b200.h).
+
+The library is built in-tree by `cm3d_b200.build.build()` (nvcc, sm_100a) and
+loaded from `cm3d_b200/_lib/libcm3d_b200.so`.  There is no CPU fallback: if the
+library is missing or a call fails this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libcm3d_b200.so")
+ABI_VERSION = 2
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_int64
+
+# name -> argtypes (restype is int for all but the two listed below); mirrors include/cm3d_b200.h
+PROTOTYPES = {
+    "cm3d_masks_pack_dense": [_P, _P, _P, _I, _I, _P, _P],
+    "cm3d_masks_fill_rle": [_P, _P, _P, _P, _I, _I, _P, _P, _P],
+    "cm3d_masks_erode3x3": [_P, _P, _I, _I, _P, _P, _P],
+    "cm3d_aggregate_sweeps": [_P, _P, _I, _P, _P, _P, _P, _P, _P],
+    "cm3d_project_membership": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "cm3d_scan_segments": [_P, _P, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P],
+    "cm3d_compact_segments": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P],
+    "cm3d_medoid": [_P, _L, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+}
+EXPORTS = ["cm3d_abi_version", "cm3d_error_string"] + list(PROTOTYPES)
+
+_lib = None
+
+
+class Cm3dError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises (never falls back) when it is absent or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Cm3dError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  cm3d_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.cm3d_abi_version.restype = ctypes.c_int
+    lib.cm3d_error_string.restype = ctypes.c_char_p
+    lib.cm3d_error_string.argtypes = [ctypes.c_int]
+    v = lib.cm3d_abi_version()
+    if v != ABI_VERSION:
+        raise Cm3dError(f"libcm3d_b200.so has ABI {v}, python side expects {ABI_VERSION}: rebuild")
+    for name, args in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().cm3d_error_string(rc).decode()
+        raise Cm3dError(f"{what} failed: {msg} (code {rc})")
+
+
+def call(name: str, *args):
+    rc = getattr(load(), name)(*args)
+    check(rc, name)

@@ -1,0 +1,232 @@
+"""Host-side packing of FrameSpecs into the flat buffers the C-ABI consumes.
+
+A `PackedBatch` is three host buffers (pinned when CUDA is present) that go to
+the GPU with one copy each:
+
+    raw    float32   every sweep's raw points back to back (16-byte aligned starts)
+    meta   int32     all descriptor tables of include/cm3d_b200.h, back to back
+    mask   uint8     dense (H,W) uint8 masks, or COCO run lengths (uint32) + offsets
+
+plus the scalar geometry (tile / instance / word counts) that sizes the device
+workspace.  Nothing here touches point coordinates: the arithmetic of the
+reference (src/nuscenes/2d_to_3d.py:433-665) happens in the CUDA kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+from .frames import CHAIN_WORDS, FOURTH_NONE, FrameSpec, RLEMask, encode_chain
+from .rle import rle_counts_to_runs
+
+TILE = 1024
+MAX_INST = 254
+MAX_VCAMS = 16
+MEDOID_COLS = 256
+SW_WORDS, FR_WORDS, VC_WORDS, IN_WORDS, ERR_WORDS = 8, 12, 20, 8, 4
+
+
+def _split64(v: int):
+    """int64 -> (lo, hi) as signed int32 words (device side: join64)."""
+    lo, hi = v & 0xFFFFFFFF, (v >> 32) & 0xFFFFFFFF
+    return (lo - (1 << 32) if lo >= (1 << 31) else lo), (hi - (1 << 32) if hi >= (1 << 31) else hi)
+
+
+def _f32_bits(x) -> int:
+    return int(np.float32(x).view(np.int32))
+
+
+def _alloc(n, dtype, pin):
+    """Host buffer of n elements; pinned torch memory when asked and possible."""
+    n = max(int(n), 1)
+    if pin:
+        import torch
+        t = torch.empty(n, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+        return t.numpy(), t
+    a = np.empty(n, dtype)
+    return a, None
+
+
+@dataclass
+class PackedBatch:
+    n_frames: int
+    n_sweeps: int
+    n_tiles: int
+    n_vcams: int
+    n_inst: int
+    n_chains: int
+    max_inst_per_frame: int
+    cnt_total: int                  # sum over frames of tiles(f) * instances(f)
+    bits_words: int                 # total words of one set of bit planes
+    max_words: int                  # largest single plane
+    n_raw_points: int
+    masks_kind: str                 # "dense" | "rle"
+    max_runs: int
+    raw: np.ndarray                 # float32
+    meta: np.ndarray                # int32
+    mask: np.ndarray                # uint8 (dense bytes) or uint32 (runs)
+    mask_off: np.ndarray            # int64: src_off[n_inst] or run_off[n_inst+1]
+    off: Dict[str, int] = field(default_factory=dict)       # table name -> int32 offset in meta
+    frame_inst: np.ndarray = None   # (F+1,) instance ranges
+    frame_vcam_cams: List[List[tuple]] = field(default_factory=list)  # per frame [(cam, W, H)]
+    tensors: dict = field(default_factory=dict)             # pinned torch views of raw/meta/mask/mask_off
+    algo_bytes: dict = field(default_factory=dict)          # algorithmic bytes per kernel
+
+    def table(self, name: str, words: int = 1) -> np.ndarray:
+        o, n = self.off[name], self.off[name + "_n"]
+        v = self.meta[o:o + n]
+        return v.reshape(-1, words) if words > 1 else v
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(self.raw.nbytes + self.meta.nbytes + self.mask.nbytes + self.mask_off.nbytes)
+
+
+def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
+    F = len(frames)
+    if F == 0:
+        raise ValueError("empty batch")
+    kinds = {("dense" if isinstance(f.masks, np.ndarray) else "rle") for f in frames if f.n_instances}
+    masks_kind = "dense" if kinds == {"dense"} else "rle"
+
+    # ---- geometry pass
+    n_sweeps = sum(len(f.sweeps) for f in frames)
+    n_inst = sum(f.n_instances for f in frames)
+    sweep_tiles, raw_off = [], []
+    ro = 0
+    for f in frames:
+        for s in f.sweeps:
+            if s.shape[0] == 0:
+                sweep_tiles.append(0)
+                raw_off.append(ro)
+                continue
+            sweep_tiles.append(-(-s.shape[0] // TILE))
+            raw_off.append(ro)
+            ro += (s.size + 3) & ~3
+    n_tiles = int(sum(sweep_tiles))
+    raw, raw_t = _alloc(ro + 4, np.float32, pin)
+    raw[ro:] = 0
+
+    sweep_desc = np.zeros((max(n_sweeps, 1), SW_WORDS), np.int32)
+    frame_desc = np.zeros((F, FR_WORDS), np.int32)
+    tile_sweep = np.zeros(max(n_tiles, 1), np.int32)
+    inst_desc = np.zeros((max(n_inst, 1), IN_WORDS), np.int32)
+    cam_inst_list = np.zeros(max(n_inst, 1), np.int32)
+    chains: List[np.ndarray] = []
+    vcam_rows: List[np.ndarray] = []
+    frame_vcam_cams = []
+    frame_inst = np.zeros(F + 1, np.int64)
+
+    si = ti = ii = 0
+    cnt_total = bits_words = max_words = 0
+    max_inst_pf = 0
+    mask_chunks, mask_off = [], [0]
+    max_runs = 0
+    for fi, f in enumerate(frames):
+        I = f.n_instances
+        if I > MAX_INST:
+            raise ValueError(f"frame {fi}: {I} instances > {MAX_INST} (CM3D_ELIMIT)")
+        max_inst_pf = max(max_inst_pf, I)
+        t_begin = ti
+        for s_local, (s, ops) in enumerate(zip(f.sweeps, f.sweep_ops)):
+            nt = sweep_tiles[si]
+            o = raw_off[si]
+            raw[o:o + s.size] = s.reshape(-1)
+            pad = ((s.size + 3) & ~3) - s.size
+            if pad:
+                raw[o + s.size:o + s.size + pad] = 0
+            sweep_desc[si] = [*_split64(o), s.shape[0], s.shape[1], fi, ti, len(chains), f.fourth]
+            chains.append(encode_chain(ops))
+            tile_sweep[ti:ti + nt] = si
+            ti += nt
+            si += 1
+        ntf = ti - t_begin
+        # vcams: unique (camera, W, H) among the frame's instances
+        sizes = [f.mask_size(i) for i in range(I)]
+        keys = sorted({(int(f.cam_nums[i]),) + sizes[i] for i in range(I)})
+        if len(keys) > MAX_VCAMS:
+            raise ValueError(f"frame {fi}: {len(keys)} (camera, mask size) pairs > {MAX_VCAMS} (CM3D_ELIMIT)")
+        v_begin = len(vcam_rows)
+        lb = 0
+        key_index = {k: n for n, k in enumerate(keys)}
+        members = [[] for _ in keys]
+        for i in range(I):
+            members[key_index[(int(f.cam_nums[i]),) + sizes[i]]].append(i)
+        for k, mem in zip(keys, members):
+            cam = f.cams[k[0]]
+            row = np.zeros(VC_WORDS, np.int32)
+            row[0] = len(chains)
+            chains.append(encode_chain(cam.ops))
+            row[1:13] = cam.viewpad34().reshape(-1).view(np.int32)
+            row[13], row[14], row[15], row[16] = k[1], k[2], lb, len(mem)
+            cam_inst_list[ii + lb: ii + lb + len(mem)] = mem
+            lb += len(mem)
+            vcam_rows.append(row)
+        frame_vcam_cams.append(keys)
+        use_close = f.close_thresh is not None
+        min_pts = 4 if f.dataset == "kitti" else 1          # kitti/2d_to_3d.py:1479-1480 skips M <= 3
+        frame_desc[fi] = [t_begin, ti, v_begin, len(keys), ii, I,
+                          _f32_bits(f.close_thresh if use_close else 0.0), int(use_close),
+                          _f32_bits(f.min_dist_f32()), cnt_total, min_pts, ii]
+        cnt_total += ntf * I
+        for i in range(I):
+            W, H = sizes[i]
+            pitch = (W + 31) // 32
+            words = pitch * H
+            inst_desc[ii + i] = [*_split64(bits_words), W, H, pitch,
+                                 v_begin + key_index[(int(f.cam_nums[i]),) + sizes[i]], fi, i]
+            bits_words += words
+            max_words = max(max_words, words)
+            if masks_kind == "dense":
+                m = f.masks[i]
+                if m.shape != (H, W):
+                    raise ValueError("dense mask shape mismatch")
+                mask_chunks.append(np.ascontiguousarray(m, np.uint8).reshape(-1))
+                mask_off.append(mask_off[-1] + ((H * W + 15) & ~15))
+            else:
+                rle = f.masks[i]
+                if isinstance(f.masks, np.ndarray):
+                    from .synthetic import dense_to_rle
+                    rle = dense_to_rle(f.masks[i][None])[0]
+                runs = rle_counts_to_runs(rle.counts)
+                mask_chunks.append(runs)
+                mask_off.append(mask_off[-1] + len(runs))
+                max_runs = max(max_runs, len(runs))
+        ii += I
+        frame_inst[fi + 1] = ii
+
+    if masks_kind == "dense":
+        mask, mask_t = _alloc(mask_off[-1], np.uint8, pin)
+        for c, o in zip(mask_chunks, mask_off[:-1]):
+            mask[o:o + c.size] = c
+        mask_off_arr = np.asarray(mask_off[:-1] if n_inst else [0], np.int64)
+    else:
+        mask, mask_t = _alloc(mask_off[-1], np.uint32, pin)
+        if mask_chunks:
+            np.concatenate(mask_chunks, out=mask[:mask_off[-1]])
+        mask_off_arr = np.asarray(mask_off, np.int64)
+
+    chains_arr = np.stack(chains).astype(np.uint32) if chains else np.zeros((1, CHAIN_WORDS), np.uint32)
+    vcam_desc = np.stack(vcam_rows) if vcam_rows else np.zeros((1, VC_WORDS), np.int32)
+    tables = [("tile_sweep", tile_sweep), ("sweep_desc", sweep_desc), ("frame_desc", frame_desc),
+              ("vcam_desc", vcam_desc), ("cam_inst_list", cam_inst_list), ("inst_desc", inst_desc),
+              ("chains", chains_arr.view(np.int32))]
+    off, pos = {}, 0
+    for name, arr in tables:
+        off[name] = pos
+        off[name + "_n"] = arr.size
+        pos += (arr.size + 3) & ~3            # keep every table 16-byte aligned
+    meta, meta_t = _alloc(pos, np.int32, pin)
+    for name, arr in tables:
+        meta[off[name]: off[name] + arr.size] = arr.reshape(-1)
+
+    mo, mo_t = _alloc(mask_off_arr.size, np.int64, pin)
+    mo[:mask_off_arr.size] = mask_off_arr
+
+    pb = PackedBatch(F, n_sweeps, n_tiles, len(vcam_rows), n_inst, len(chains), max_inst_pf, cnt_total,
+                     bits_words, max_words, sum(f.n_raw_points for f in frames), masks_kind, max_runs,
+                     raw, meta, mask, mo[:mask_off_arr.size], off, frame_inst, frame_vcam_cams,
+                     {"raw": raw_t, "meta": meta_t, "mask": mask_t, "mask_off": mo_t})
+    return pb

@@ -1,0 +1,45 @@
+"""In-tree build of the CUDA library: nvcc -> cm3d_b200/_lib/libcm3d_b200.so (sm_100a only).
+
+`-fmad=false`: every FMA the arithmetic needs is written as an explicit
+`__fmaf_rn`; nothing else may be contracted (DESIGN.md "Numerics").
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+OUT_DIR = os.path.join(_HERE, "_lib")
+OUT = os.path.join(OUT_DIR, "libcm3d_b200.so")
+SOURCES = ["masks.cu", "lift.cu", "medoid.cu"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-fmad=false", "-shared", "-Xcompiler", "-fPIC"]
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(_HERE, "..", "include", "cm3d_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

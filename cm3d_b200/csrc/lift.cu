@@ -1,0 +1,598 @@
+// Sweeps -> aggregated cloud -> per-camera projection -> mask membership -> ordered
+// per-instance segments, for a whole batch of frames per launch.
+//
+// Replaces (and runs ONCE per frame and camera what the reference redoes per mask):
+//   k_aggregate        src/nuscenes/2d_to_3d.py:437-465  close-point filter, rotate/translate
+//                      chain per sweep (utils/pcd.py:159-172), hstack;
+//                      src/kitti/2d_to_3d.py:1066-1077 (project_velo_to_ref);
+//                      src/waymo/2d_to_3d.py:472-481 (xyz + ones row)
+//   k_project_count    src/nuscenes/2d_to_3d.py:553-613  clone, global->camera chain,
+//                      view_points (utils/pcd.py:262-284), depth/bounds test, floor,
+//                      mask lookup incl. the `logical_and(floored_points, ...)` quirk;
+//                      src/kitti/2d_to_3d.py:1238-1351; src/waymo/2d_to_3d.py:557-616
+//   k_scan_* / k_compact  src/nuscenes/2d_to_3d.py:615-620  track_points (ascending point
+//                      index per instance) and `aggr_pc_points[:, track_points]`
+//
+// All of it is HBM-bound streaming work: raw tiles are staged with one bulk async copy
+// (TMA, UBLKCP) per tile, the cloud lives as SoA (x|y|z|w) read with 128-bit loads, and
+// order-preserving compaction uses warp ballots + small scans instead of atomics on HBM.
+#include "common.cuh"
+
+namespace cm3d {
+
+constexpr int kGroups = kTile / 32;   // 32-slot groups per tile
+
+// ------------------------------------------------------------------------------------------
+// K1: one block per raw tile.
+__global__ void __launch_bounds__(kBlock)
+k_aggregate(const float *__restrict__ raw, const int32_t *__restrict__ tile_sweep,
+            const int32_t *__restrict__ sweep_desc, const int32_t *__restrict__ frame_desc,
+            const uint32_t *__restrict__ chains, float *__restrict__ xyzw, int64_t n_slots,
+            int32_t *__restrict__ tile_cnt)
+{
+    __shared__ __align__(128) float s_raw[kTile * 5];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_chain[CM3D_CHAIN_WORDS];
+    __shared__ int s_gcnt[kGroups];
+
+    const int t = blockIdx.x;
+    const int32_t *sd = sweep_desc + (size_t)tile_sweep[t] * CM3D_SW_WORDS;
+    const int stride = sd[CM3D_SW_STRIDE];
+    const int p0 = (t - sd[CM3D_SW_TILE_BASE]) * kTile;
+    const int npts = min(kTile, sd[CM3D_SW_NPTS] - p0);
+    const int fourth = sd[CM3D_SW_FOURTH];
+    const int32_t *fd = frame_desc + (size_t)sd[CM3D_SW_FRAME] * CM3D_FR_WORDS;
+    const bool use_close = fd[CM3D_FR_USE_CLOSE] != 0;
+    const float close_thr = __int_as_float(fd[CM3D_FR_CLOSE_BITS]);
+    const float *src = raw + join64(sd[CM3D_SW_RAW_LO], sd[CM3D_SW_RAW_HI]) + (int64_t)p0 * stride;
+
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    if (threadIdx.x < CM3D_CHAIN_WORDS)
+        s_chain[threadIdx.x] = chains[(size_t)sd[CM3D_SW_CHAIN] * CM3D_CHAIN_WORDS + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // sweeps start 16-byte aligned and are padded to 16 bytes, tiles are 1024*stride*4 bytes
+        const uint32_t bytes = (uint32_t)(((npts * stride * 4) + 15) & ~15);
+        mbar_expect_tx(&s_bar, bytes);
+        bulk_g2s(s_raw, src, bytes, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    float px[kPerThread], py[kPerThread], pz[kPerThread], pw[kPerThread];
+    unsigned ball[kPerThread];
+#pragma unroll
+    for (int r = 0; r < kPerThread; ++r) {
+        const int p = r * kBlock + threadIdx.x;
+        bool keep = p < npts;
+        float x = 0.f, y = 0.f, z = 0.f, w = 1.0f;
+        if (keep) {
+            const float *q = s_raw + p * stride;
+            x = q[0]; y = q[1]; z = q[2];
+            if (fourth == 1) w = q[3];
+            if (use_close && fabsf(x) < close_thr && fabsf(y) < close_thr) keep = false;
+        }
+        px[r] = x; py[r] = y; pz[r] = z; pw[r] = w;
+        ball[r] = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_gcnt[r * (kBlock / 32) + warp] = __popc(ball[r]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int c = s_gcnt[lane];
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += v;
+        }
+        s_gcnt[lane] = inc - c;
+        if (lane == 31) tile_cnt[t] = inc;
+    }
+    __syncthreads();
+    float *ox = xyzw, *oy = xyzw + n_slots, *oz = xyzw + 2 * n_slots, *ow = xyzw + 3 * n_slots;
+#pragma unroll
+    for (int r = 0; r < kPerThread; ++r) {
+        if (ball[r] & (1u << lane)) {
+            const int64_t slot = (int64_t)t * kTile + s_gcnt[r * (kBlock / 32) + warp] + __popc(ball[r] & lanemask_lt());
+            float x = px[r], y = py[r], z = pz[r];
+            apply_chain(s_chain, x, y, z);
+            ox[slot] = x; oy[slot] = y; oz[slot] = z;
+            if (fourth) ow[slot] = pw[r];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-frame tables staged in shared memory by the membership kernels.
+struct VcamS {
+    uint32_t chain[CM3D_CHAIN_WORDS];
+    float vp[12];
+    float wlim, hlim;      // float(W-1), float(H-1)
+    int list_begin, list_count;
+};
+struct InstS {
+    int xmin, ymin, xmax, ymax;   // eroded bbox, clamped to >= 1 (the reference drops fx==0 / fy==0)
+    const uint32_t *plane;
+    int pitch, pad;
+};
+
+struct FrameTables {
+    VcamS vcam[CM3D_MAX_VCAMS];
+    InstS inst[CM3D_MAX_INST + 2];
+    uint8_t list[CM3D_MAX_INST + 2];
+    int n_vcams, n_inst;
+    float min_depth;
+};
+
+__device__ __forceinline__ void load_frame_tables(FrameTables &ft, const int32_t *__restrict__ fd,
+                                                  const int32_t *__restrict__ vcam_desc,
+                                                  const int32_t *__restrict__ cam_inst_list,
+                                                  const int32_t *__restrict__ inst_desc,
+                                                  const int32_t *__restrict__ inst_bbox,
+                                                  const uint32_t *__restrict__ chains,
+                                                  const uint32_t *__restrict__ bits)
+{
+    const int nv = fd[CM3D_FR_NVCAMS], ni = fd[CM3D_FR_NINST];
+    const int v0 = fd[CM3D_FR_VCAM_BEGIN], i0 = fd[CM3D_FR_INST_BEGIN], l0 = fd[CM3D_FR_LIST_BEGIN];
+    if (threadIdx.x == 0) {
+        ft.n_vcams = nv;
+        ft.n_inst = ni;
+        ft.min_depth = __int_as_float(fd[CM3D_FR_MIN_DEPTH_BITS]);
+    }
+    for (int k = threadIdx.x; k < nv * CM3D_CHAIN_WORDS; k += blockDim.x) {
+        const int v = k / CM3D_CHAIN_WORDS, wd = k - v * CM3D_CHAIN_WORDS;
+        const int32_t *vd = vcam_desc + (size_t)(v0 + v) * CM3D_VC_WORDS;
+        ft.vcam[v].chain[wd] = chains[(size_t)vd[CM3D_VC_CHAIN] * CM3D_CHAIN_WORDS + wd];
+    }
+    for (int k = threadIdx.x; k < nv * 16; k += blockDim.x) {
+        const int v = k >> 4, wd = k & 15;
+        const int32_t *vd = vcam_desc + (size_t)(v0 + v) * CM3D_VC_WORDS;
+        if (wd < 12) ft.vcam[v].vp[wd] = __int_as_float(vd[CM3D_VC_VIEWPAD + wd]);
+        else if (wd == 12) ft.vcam[v].wlim = (float)(vd[CM3D_VC_W] - 1);
+        else if (wd == 13) ft.vcam[v].hlim = (float)(vd[CM3D_VC_H] - 1);
+        else if (wd == 14) ft.vcam[v].list_begin = vd[CM3D_VC_LIST_BEGIN];
+        else ft.vcam[v].list_count = vd[CM3D_VC_LIST_COUNT];
+    }
+    for (int j = threadIdx.x; j < ni; j += blockDim.x) {
+        const int32_t *d = inst_desc + (size_t)(i0 + j) * CM3D_IN_WORDS;
+        const int32_t *bb = inst_bbox + (size_t)(i0 + j) * 4;
+        InstS s;
+        s.xmin = max(bb[0], 1); s.ymin = max(bb[1], 1); s.xmax = bb[2]; s.ymax = bb[3];
+        s.plane = bits + join64(d[CM3D_IN_BITS_LO], d[CM3D_IN_BITS_HI]);
+        s.pitch = d[CM3D_IN_PITCH];
+        s.pad = 0;
+        ft.inst[j] = s;
+        ft.list[j] = (uint8_t)cam_inst_list[l0 + j];
+    }
+}
+
+// Project one point into vcam `vc`; returns fx | fy<<16, or -1 when it fails the reference's
+// `depths > min_dist, 0 < u < W-1, 0 < v < H-1` test (nuscenes:597-603).
+__device__ __forceinline__ int32_t project_point(const VcamS &vc, float min_depth, float x, float y, float z)
+{
+    apply_chain(vc.chain, x, y, z);
+    if (!(z > min_depth)) return -1;
+    const float *m = vc.vp;
+    const float r0 = __fmaf_rn(m[3], 1.0f, __fmaf_rn(m[2], z, __fmaf_rn(m[1], y, __fmul_rn(m[0], x))));
+    const float r1 = __fmaf_rn(m[7], 1.0f, __fmaf_rn(m[6], z, __fmaf_rn(m[5], y, __fmul_rn(m[4], x))));
+    const float r2 = __fmaf_rn(m[11], 1.0f, __fmaf_rn(m[10], z, __fmaf_rn(m[9], y, __fmul_rn(m[8], x))));
+    const float u = __fdiv_rn(r0, r2), v = __fdiv_rn(r1, r2);
+    if (u > 0.0f && u < vc.wlim && v > 0.0f && v < vc.hlim)
+        return (int32_t)floorf(u) | ((int32_t)floorf(v) << 16);
+    return -1;
+}
+
+// Calls f(j) for every instance j (frame-local) the point belongs to; within one vcam the ids
+// come in ascending order.
+template <class F>
+__device__ __forceinline__ void for_each_hit(const FrameTables &ft, float x, float y, float z, int32_t *pix,
+                                             int64_t pix_stride, F f)
+{
+    for (int v = 0; v < ft.n_vcams; ++v) {
+        const VcamS &vc = ft.vcam[v];
+        const int32_t code = project_point(vc, ft.min_depth, x, y, z);
+        if (pix) pix[v * pix_stride] = code;
+        if (code < 0) continue;
+        const int fx = code & 0xffff, fy = code >> 16;
+        const int e = vc.list_begin + vc.list_count;
+        for (int k = vc.list_begin; k < e; ++k) {
+            const int j = ft.list[k];
+            const InstS &s = ft.inst[j];
+            if (fx < s.xmin || fx > s.xmax || fy < s.ymin || fy > s.ymax) continue;
+            const uint32_t wd = __ldg(s.plane + (size_t)fy * s.pitch + (fx >> 5));
+            if ((wd >> (fx & 31)) & 1u) f(j);
+        }
+    }
+}
+
+// Sorted insert of id (1..254) into a 4-byte hit word; byte 3 becomes 255 on overflow.
+__device__ __forceinline__ uint32_t hit_insert(uint32_t hw, uint32_t id)
+{
+    if (hw >> 24) return hw | 0xff000000u;          // already four (or overflowed)
+    // shift bytes greater than id up by one
+    uint32_t out = 0, placed = 0;
+    int pos = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const uint32_t cur = (hw >> (8 * b)) & 0xffu;
+        if (cur == 0) break;
+        if (!placed && id < cur) { out |= id << (8 * pos++); placed = 1; }
+        out |= cur << (8 * pos++);
+    }
+    if (!placed) out |= id << (8 * pos);
+    return out;
+}
+
+// K2 (count pass): one block per tile of the aggregated cloud.
+__global__ void __launch_bounds__(kBlock)
+k_project_count(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *__restrict__ tile_cnt,
+                const int32_t *__restrict__ tile_sweep, const int32_t *__restrict__ sweep_desc,
+                const int32_t *__restrict__ frame_desc, const int32_t *__restrict__ vcam_desc,
+                const int32_t *__restrict__ cam_inst_list, const int32_t *__restrict__ inst_desc,
+                const int32_t *__restrict__ inst_bbox, const uint32_t *__restrict__ chains,
+                const uint32_t *__restrict__ bits, uint32_t *__restrict__ hits,
+                uint16_t *__restrict__ tile_inst_cnt, int32_t *__restrict__ pix)
+{
+    __shared__ FrameTables ft;
+    __shared__ int s_hist[CM3D_MAX_INST + 2];
+
+    const int t = blockIdx.x;
+    const int f = sweep_desc[(size_t)tile_sweep[t] * CM3D_SW_WORDS + CM3D_SW_FRAME];
+    const int32_t *fd = frame_desc + (size_t)f * CM3D_FR_WORDS;
+    load_frame_tables(ft, fd, vcam_desc, cam_inst_list, inst_desc, inst_bbox, chains, bits);
+    for (int j = threadIdx.x; j < CM3D_MAX_INST + 2; j += blockDim.x) s_hist[j] = 0;
+    __syncthreads();
+
+    const int cnt = tile_cnt[t];
+    const int64_t base = (int64_t)t * kTile;
+    const int s0 = threadIdx.x * 4;
+    if (s0 < cnt) {
+        const float4 X = __ldg(reinterpret_cast<const float4 *>(xyzw + base + s0));
+        const float4 Y = __ldg(reinterpret_cast<const float4 *>(xyzw + n_slots + base + s0));
+        const float4 Z = __ldg(reinterpret_cast<const float4 *>(xyzw + 2 * n_slots + base + s0));
+        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+        uint32_t hw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (s0 + k >= cnt) break;
+            uint32_t h = 0;
+            for_each_hit(ft, xs[k], ys[k], zs[k], pix ? pix + base + s0 + k : nullptr, n_slots, [&](int j) {
+                h = hit_insert(h, (uint32_t)j + 1u);
+                atomicAdd(&s_hist[j], 1);
+            });
+            hw[k] = h;
+        }
+        *reinterpret_cast<uint4 *>(hits + base + s0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    }
+    __syncthreads();
+    const int tl = t - fd[CM3D_FR_TILE_BEGIN], ntf = fd[CM3D_FR_TILE_END] - fd[CM3D_FR_TILE_BEGIN];
+    uint16_t *out = tile_inst_cnt + (size_t)fd[CM3D_FR_CNT_OFF] + tl;
+    for (int j = threadIdx.x; j < ft.n_inst; j += blockDim.x) out[(size_t)j * ntf] = (uint16_t)s_hist[j];
+}
+
+// ------------------------------------------------------------------------------------------
+// Scans.  k_scan_rows: one warp per (frame, row); rows 0..n_inst-1 are instances (prefix of
+// tile_inst_cnt over the frame's tiles), row n_inst is the tile occupancy (tile_prefix).
+__global__ void __launch_bounds__(256)
+k_scan_rows(const int32_t *__restrict__ tile_cnt, const uint16_t *__restrict__ tile_inst_cnt,
+            const int32_t *__restrict__ frame_desc, int32_t *__restrict__ tile_prefix,
+            int32_t *__restrict__ frame_n, int32_t *__restrict__ tile_inst_base,
+            int32_t *__restrict__ seg_count)
+{
+    const int f = blockIdx.x;
+    const int row = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int32_t *fd = frame_desc + (size_t)f * CM3D_FR_WORDS;
+    const int ni = fd[CM3D_FR_NINST];
+    if (row > ni) return;
+    const int tb = fd[CM3D_FR_TILE_BEGIN], ntf = fd[CM3D_FR_TILE_END] - tb;
+    const unsigned lane = lane_id();
+    const bool is_tiles = row == ni;
+    const uint16_t *src16 = tile_inst_cnt + (size_t)fd[CM3D_FR_CNT_OFF] + (size_t)row * ntf;
+    int32_t *dst = is_tiles ? tile_prefix + tb : tile_inst_base + (size_t)fd[CM3D_FR_CNT_OFF] + (size_t)row * ntf;
+    int run = 0;
+    for (int c = 0; c < ntf; c += 32) {
+        const int k = c + lane;
+        const int v = k < ntf ? (is_tiles ? tile_cnt[tb + k] : (int)src16[k]) : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += u;
+        }
+        if (k < ntf) dst[k] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) {
+        if (is_tiles) frame_n[f] = run;
+        else seg_count[fd[CM3D_FR_INST_BEGIN] + row] = run;
+    }
+}
+
+// k_scan_batch: one block; seg_off / item_off over all instances of the batch.
+__global__ void __launch_bounds__(1024)
+k_scan_batch(const int32_t *__restrict__ seg_count, const int32_t *__restrict__ inst_desc,
+             const int32_t *__restrict__ frame_desc, int n_inst_total, int64_t seg_cap,
+             int32_t *__restrict__ seg_off, int32_t *__restrict__ item_off,
+             unsigned long long *__restrict__ medoid_best, int32_t *__restrict__ errflags)
+{
+    __shared__ long long s_wa[32];
+    __shared__ int s_wb[32];
+    __shared__ long long s_ca;
+    __shared__ int s_cb;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_ca = 0; s_cb = 0; }
+    __syncthreads();
+    for (int base = 0; base < n_inst_total; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        long long a = 0;
+        int b = 0;
+        if (i < n_inst_total) {
+            const int m = seg_count[i];
+            const int f = inst_desc[(size_t)i * CM3D_IN_WORDS + CM3D_IN_FRAME];
+            const int minp = max(frame_desc[(size_t)f * CM3D_FR_WORDS + CM3D_FR_MIN_MEDOID_PTS], 1);
+            a = m;
+            b = m >= minp ? (m + CM3D_MEDOID_COLS - 1) / CM3D_MEDOID_COLS : 0;
+            medoid_best[i] = ~0ull;
+        }
+        long long ia = a;
+        int ib = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long ua = __shfl_up_sync(0xffffffffu, ia, o);
+            const int ub = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= (unsigned)o) { ia += ua; ib += ub; }
+        }
+        if (lane == 31) { s_wa[warp] = ia; s_wb[warp] = ib; }
+        __syncthreads();
+        long long oa = s_ca;
+        int ob = s_cb;
+        for (unsigned w = 0; w < warp; ++w) { oa += s_wa[w]; ob += s_wb[w]; }
+        if (i < n_inst_total) {
+            const long long ex = oa + ia - a;
+            seg_off[i] = (int32_t)min(ex, (long long)0x7fffffff);
+            item_off[i] = ob + ib - b;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) { s_ca = oa + ia; s_cb = ob + ib; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        seg_off[n_inst_total] = (int32_t)min(s_ca, (long long)0x7fffffff);
+        item_off[n_inst_total] = s_cb;
+        if (s_ca > seg_cap) errflags[CM3D_ERR_SEG_OVERFLOW] = (int32_t)min(s_ca, (long long)0x7fffffff);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (write pass): one block per tile.  Ranks inside a tile come from warp ballots taken in
+// ascending instance order per 32-slot group, so every segment is in ascending point order.
+// The ballot walk runs twice: once to count members per (group, instance), once - after an
+// exclusive prefix over the groups - to scatter.
+struct PendingHits {
+    uint32_t word;       // up to four ids, ascending, one per byte (non-overflow points)
+    uint32_t bm[8];      // membership bitmask of an overflow point (more than four masks)
+    bool ovf;
+    __device__ __forceinline__ uint32_t front() const
+    {
+        if (!ovf) return word & 0xffu;
+        for (int w = 0; w < 8; ++w)
+            if (bm[w]) return (uint32_t)(w * 32 + __ffs(bm[w]));   // id = j + 1
+        return 0u;
+    }
+    __device__ __forceinline__ void pop()
+    {
+        if (!ovf) { word >>= 8; return; }
+        for (int w = 0; w < 8; ++w)
+            if (bm[w]) { bm[w] &= bm[w] - 1u; return; }
+    }
+};
+
+__global__ void __launch_bounds__(kBlock)
+k_compact(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *__restrict__ tile_cnt,
+          const int32_t *__restrict__ tile_prefix, const int32_t *__restrict__ tile_sweep,
+          const int32_t *__restrict__ sweep_desc, const int32_t *__restrict__ frame_desc,
+          const int32_t *__restrict__ vcam_desc, const int32_t *__restrict__ cam_inst_list,
+          const int32_t *__restrict__ inst_desc, const int32_t *__restrict__ inst_bbox,
+          const uint32_t *__restrict__ chains, const uint32_t *__restrict__ bits,
+          const uint32_t *__restrict__ hits, const int32_t *__restrict__ tile_inst_base,
+          const int32_t *__restrict__ seg_off, int32_t *__restrict__ seg_point_idx,
+          float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *__restrict__ errflags)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];   // [kGroups][ni] u16, then [ni] int
+    __shared__ FrameTables ft;                                    // only filled on the overflow path
+    __shared__ int s_any, s_ovf;
+
+    if (errflags[CM3D_ERR_SEG_OVERFLOW] != 0) return;
+    const int t = blockIdx.x;
+    const int cnt = tile_cnt[t];
+    const int32_t *sd = sweep_desc + (size_t)tile_sweep[t] * CM3D_SW_WORDS;
+    const int32_t *fd = frame_desc + (size_t)sd[CM3D_SW_FRAME] * CM3D_FR_WORDS;
+    const int ni = fd[CM3D_FR_NINST];
+    const int fourth = sd[CM3D_SW_FOURTH];
+    const int64_t base = (int64_t)t * kTile;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+
+    // group g = r*8 + warp covers slots [g*32, g*32+32)
+    uint32_t hw[kPerThread];
+    bool any = false, ovf = false;
+#pragma unroll
+    for (int r = 0; r < kPerThread; ++r) {
+        const int s = r * kBlock + threadIdx.x;
+        hw[r] = s < cnt ? __ldg(hits + base + s) : 0u;
+        any |= hw[r] != 0;
+        ovf |= (hw[r] >> 24) == 0xffu;
+    }
+    if (threadIdx.x == 0) { s_any = 0; s_ovf = 0; }
+    __syncthreads();
+    if (any) s_any = 1;
+    if (ovf) s_ovf = 1;
+    __syncthreads();
+    if (!s_any) return;
+
+    uint16_t *s_gc = reinterpret_cast<uint16_t *>(dyn_smem);
+    int *s_base = reinterpret_cast<int *>(dyn_smem + ((kGroups * ni * 2 + 15) & ~15));
+    for (int k = threadIdx.x; k < kGroups * ni; k += blockDim.x) s_gc[k] = 0;
+    const int tl = t - fd[CM3D_FR_TILE_BEGIN], ntf = fd[CM3D_FR_TILE_END] - fd[CM3D_FR_TILE_BEGIN];
+    for (int j = threadIdx.x; j < ni; j += blockDim.x)
+        s_base[j] = seg_off[fd[CM3D_FR_INST_BEGIN] + j] +
+                    tile_inst_base[(size_t)fd[CM3D_FR_CNT_OFF] + (size_t)j * ntf + tl];
+    const bool have_ovf = s_ovf != 0;
+    if (have_ovf) load_frame_tables(ft, fd, vcam_desc, cam_inst_list, inst_desc, inst_bbox, chains, bits);
+    __syncthreads();
+
+    const float *gx = xyzw, *gy = xyzw + n_slots, *gz = xyzw + 2 * n_slots, *gw = xyzw + 3 * n_slots;
+    float *sx = seg_xyzw, *sy = seg_xyzw + seg_cap, *sz = seg_xyzw + 2 * seg_cap, *sw = seg_xyzw + 3 * seg_cap;
+    const int tp = tile_prefix[t];
+
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int r = 0; r < kPerThread; ++r) {
+            const int s = r * kBlock + threadIdx.x;
+            const int g = r * (kBlock / 32) + warp;
+            if (!__any_sync(0xffffffffu, hw[r] != 0)) continue;
+            float x = 0.f, y = 0.f, z = 0.f, w = 0.f;
+            PendingHits ph;
+            ph.word = hw[r];
+            ph.ovf = (hw[r] >> 24) == 0xffu;
+            if (hw[r] != 0 && (pass == 1 || ph.ovf)) {
+                x = gx[base + s]; y = gy[base + s]; z = gz[base + s];
+                if (fourth) w = gw[base + s];
+            }
+            if (have_ovf && ph.ovf) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) ph.bm[q] = 0u;
+                for_each_hit(ft, x, y, z, nullptr, 0, [&](int j) { ph.bm[j >> 5] |= 1u << (j & 31); });
+            }
+            while (true) {
+                const uint32_t mine = ph.front();                 // smallest pending id, 0 = none
+                const uint32_t jmin = __reduce_min_sync(0xffffffffu, mine ? mine : 0xffffu);
+                if (jmin == 0xffffu) break;
+                const int j = (int)jmin - 1;
+                const unsigned m = __ballot_sync(0xffffffffu, mine == jmin);
+                if (pass == 0) {
+                    if (lane == 0) s_gc[g * ni + j] = (uint16_t)__popc(m);
+                } else if (mine == jmin) {
+                    const int64_t dst = (int64_t)s_base[j] + s_gc[g * ni + j] + __popc(m & lanemask_lt());
+                    if (dst < seg_cap) {
+                        seg_point_idx[dst] = tp + s;
+                        sx[dst] = x; sy[dst] = y; sz[dst] = z; sw[dst] = w;
+                    }
+                }
+                if (mine == jmin) ph.pop();
+            }
+        }
+        if (pass == 0) {
+            __syncthreads();
+            // exclusive prefix over the groups, per instance
+            for (int j = threadIdx.x; j < ni; j += blockDim.x) {
+                int run = 0;
+                for (int g = 0; g < kGroups; ++g) {
+                    const int c = s_gc[g * ni + j];
+                    s_gc[g * ni + j] = (uint16_t)run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace cm3d
+
+using namespace cm3d;
+
+extern "C" int cm3d_abi_version(void) { return CM3D_ABI_VERSION; }
+
+extern "C" const char *cm3d_error_string(int code)
+{
+    if (code == CM3D_OK) return "ok";
+    if (code == CM3D_EINVAL) return "invalid argument";
+    if (code == CM3D_ELIMIT) return "per-frame limit exceeded (instances > 254 or vcams > 16)";
+    if (code <= -1000) return cudaGetErrorString((cudaError_t)(-code - 1000));
+    return "unknown cm3d error";
+}
+
+extern "C" int cm3d_aggregate_sweeps(const float *raw, const int32_t *tile_sweep, int n_tiles,
+                                     const int32_t *sweep_desc, const int32_t *frame_desc,
+                                     const uint32_t *chains, float *xyzw, int32_t *tile_cnt, void *stream)
+{
+    if (n_tiles < 0) return CM3D_EINVAL;
+    if (n_tiles == 0) return CM3D_OK;
+    if (!raw || !tile_sweep || !sweep_desc || !frame_desc || !chains || !xyzw || !tile_cnt) return CM3D_EINVAL;
+    if (((uintptr_t)raw & 15) != 0) return CM3D_EINVAL;
+    k_aggregate<<<n_tiles, kBlock, 0, (cudaStream_t)stream>>>(raw, tile_sweep, sweep_desc, frame_desc, chains, xyzw,
+                                                              (int64_t)n_tiles * kTile, tile_cnt);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}
+
+extern "C" int cm3d_project_membership(const float *xyzw, const int32_t *tile_cnt, const int32_t *tile_sweep,
+                                       int n_tiles, const int32_t *sweep_desc, const int32_t *frame_desc,
+                                       const int32_t *vcam_desc, const int32_t *cam_inst_list,
+                                       const int32_t *inst_desc, const int32_t *inst_bbox,
+                                       const uint32_t *chains, const uint32_t *bits, uint32_t *hits,
+                                       uint16_t *tile_inst_cnt, int32_t *pix, void *stream)
+{
+    if (n_tiles < 0) return CM3D_EINVAL;
+    if (n_tiles == 0) return CM3D_OK;
+    if (!xyzw || !tile_cnt || !tile_sweep || !sweep_desc || !frame_desc || !vcam_desc || !cam_inst_list ||
+        !inst_desc || !inst_bbox || !chains || !bits || !hits || !tile_inst_cnt)
+        return CM3D_EINVAL;
+    k_project_count<<<n_tiles, kBlock, 0, (cudaStream_t)stream>>>(
+        xyzw, (int64_t)n_tiles * kTile, tile_cnt, tile_sweep, sweep_desc, frame_desc, vcam_desc, cam_inst_list,
+        inst_desc, inst_bbox, chains, bits, hits, tile_inst_cnt, pix);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}
+
+extern "C" int cm3d_scan_segments(const int32_t *tile_cnt, const uint16_t *tile_inst_cnt,
+                                  const int32_t *frame_desc, int n_frames, int max_inst_per_frame,
+                                  int n_inst_total, const int32_t *inst_desc, int64_t seg_cap,
+                                  int32_t *tile_prefix, int32_t *frame_n, int32_t *tile_inst_base,
+                                  int32_t *seg_off, int32_t *item_off, unsigned long long *medoid_best,
+                                  int32_t *errflags, void *stream)
+{
+    if (n_frames < 0 || max_inst_per_frame < 0 || n_inst_total < 0 || seg_cap < 0) return CM3D_EINVAL;
+    if (max_inst_per_frame > CM3D_MAX_INST) return CM3D_ELIMIT;
+    if (n_frames == 0) return CM3D_OK;
+    if (!tile_cnt || !tile_inst_cnt || !frame_desc || !tile_prefix || !frame_n || !tile_inst_base || !seg_off ||
+        !item_off || !medoid_best || !errflags || (n_inst_total && !inst_desc))
+        return CM3D_EINVAL;
+    // seg_count is staged in seg_off[1..] (k_scan_batch reads element i before writing it)
+    int32_t *seg_count = seg_off + 1;
+    dim3 grid(n_frames, (max_inst_per_frame + 1 + 7) / 8);
+    k_scan_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(tile_cnt, tile_inst_cnt, frame_desc, tile_prefix, frame_n,
+                                                        tile_inst_base, seg_count);
+    CM3D_LAUNCH_CHECK();
+    k_scan_batch<<<1, 1024, 0, (cudaStream_t)stream>>>(seg_count, inst_desc, frame_desc, n_inst_total, seg_cap,
+                                                       seg_off, item_off, medoid_best, errflags);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}
+
+extern "C" int cm3d_compact_segments(const float *xyzw, const int32_t *tile_cnt, const int32_t *tile_prefix,
+                                     const int32_t *tile_sweep, int n_tiles, const int32_t *sweep_desc,
+                                     const int32_t *frame_desc, const int32_t *vcam_desc,
+                                     const int32_t *cam_inst_list, const int32_t *inst_desc,
+                                     const int32_t *inst_bbox, const uint32_t *chains, const uint32_t *bits,
+                                     const uint32_t *hits, const int32_t *tile_inst_base,
+                                     const int32_t *seg_off, int32_t *seg_point_idx, float *seg_xyzw,
+                                     int64_t seg_cap, int max_inst_per_frame, const int32_t *errflags,
+                                     void *stream)
+{
+    if (n_tiles < 0 || seg_cap < 0 || max_inst_per_frame < 0) return CM3D_EINVAL;
+    if (max_inst_per_frame > CM3D_MAX_INST) return CM3D_ELIMIT;
+    if (n_tiles == 0) return CM3D_OK;
+    if (!xyzw || !tile_cnt || !tile_prefix || !tile_sweep || !sweep_desc || !frame_desc || !vcam_desc ||
+        !cam_inst_list || !inst_desc || !inst_bbox || !chains || !bits || !hits || !tile_inst_base || !seg_off ||
+        !seg_point_idx || !seg_xyzw || !errflags)
+        return CM3D_EINVAL;
+    const size_t smem = ((kGroups * max_inst_per_frame * 2 + 15) & ~15) + max_inst_per_frame * sizeof(int) + 16;
+    k_compact<<<n_tiles, kBlock, smem, (cudaStream_t)stream>>>(
+        xyzw, (int64_t)n_tiles * kTile, tile_cnt, tile_prefix, tile_sweep, sweep_desc, frame_desc, vcam_desc,
+        cam_inst_list, inst_desc, inst_bbox, chains, bits, hits, tile_inst_base, seg_off, seg_point_idx, seg_xyzw,
+        seg_cap, errflags);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}

@@ -1,0 +1,236 @@
+// Instance masks on the GPU: COCO run lengths or dense uint8 -> bit planes ->
+// 3x3-eroded bit planes + bounding boxes.
+//
+// Replaces, for a whole batch of frames at once:
+//   pycocotools.mask.decode + transpose   src/nuscenes/2d_to_3d.py:425-428, waymo:520-521
+//   cv2.erode(mask, ones((3,3)))          src/nuscenes/2d_to_3d.py:526-527, kitti:1149-1150, waymo:531-532
+//   .astype(bool) -> (W,H) torch view     src/nuscenes/2d_to_3d.py:543-544
+// A bit plane stores pixel (x, y) of the (H,W) image at bit (x & 31) of word
+// y*pitch + (x >> 5); the reference's `mask[fx, fy]` on its (W,H) view is that bit.
+// HBM-bound byte/bit work: coalesced 32-byte reads per thread, one word out.
+#include "common.cuh"
+
+namespace cm3d {
+
+// ------------------------------------------------------------------ dense uint8 -> bits
+__device__ __forceinline__ uint32_t nz4(uint32_t v)
+{
+    // one bit per non-zero byte of v, in byte order
+    return ((__vcmpne4(v, 0u) & 0x08040201u) * 0x01010101u) >> 24;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_dense(const uint8_t *__restrict__ masks, const int64_t *__restrict__ src_off,
+             const int32_t *__restrict__ inst_desc, uint32_t *__restrict__ bits)
+{
+    const int i = blockIdx.y;
+    const int32_t *d = inst_desc + i * CM3D_IN_WORDS;
+    const int W = d[CM3D_IN_W], H = d[CM3D_IN_H], pitch = d[CM3D_IN_PITCH];
+    const int wd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wd >= H * pitch) return;
+    const int y = wd / pitch, xw = wd - y * pitch, x0 = xw * 32;
+    const int64_t so = src_off[i];
+    const uint8_t *row = masks + so + (int64_t)y * W;
+    uint32_t out = 0;
+    if (((W & 31) == 0) && ((so & 15) == 0)) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(row + x0));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(row + x0 + 16));
+        out = nz4(a.x) | (nz4(a.y) << 4) | (nz4(a.z) << 8) | (nz4(a.w) << 12) |
+              (nz4(b.x) << 16) | (nz4(b.y) << 20) | (nz4(b.z) << 24) | (nz4(b.w) << 28);
+    } else {
+        const int nb = min(32, W - x0);
+        for (int b = 0; b < nb; ++b) out |= (uint32_t)(row[x0 + b] != 0) << b;
+    }
+    bits[join64(d[CM3D_IN_BITS_LO], d[CM3D_IN_BITS_HI]) + wd] = out;
+}
+
+// ------------------------------------------------------------------ COCO runs -> bits
+// run_start[r] = first flat pixel (y*W + x) of run r; one block per instance.
+__global__ void __launch_bounds__(256)
+k_rle_prefix(const uint32_t *__restrict__ runs, const int64_t *__restrict__ run_off,
+             const int32_t *__restrict__ inst_desc, uint32_t *__restrict__ run_start,
+             int32_t *__restrict__ errflags)
+{
+    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_carry;
+    const int i = blockIdx.x;
+    const int64_t r0 = run_off[i], r1 = run_off[i + 1];
+    const int32_t *d = inst_desc + i * CM3D_IN_WORDS;
+    const uint32_t total = (uint32_t)d[CM3D_IN_W] * (uint32_t)d[CM3D_IN_H];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = r0; base < r1; base += blockDim.x) {
+        const int64_t r = base + threadIdx.x;
+        const uint32_t v = r < r1 ? runs[r] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += t;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        uint32_t woff = s_carry;
+        for (unsigned w = 0; w < warp; ++w) woff += s_w[w];
+        if (r < r1) run_start[r] = woff + inc - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = woff + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && s_carry != total) atomicExch(&errflags[CM3D_ERR_RLE_SIZE], i + 1);
+}
+
+// One warp per 1-run: OR its pixels into the (zeroed) bit plane, row by row.
+__global__ void __launch_bounds__(256)
+k_rle_fill(const uint32_t *__restrict__ runs, const int64_t *__restrict__ run_off,
+           const uint32_t *__restrict__ run_start, const int32_t *__restrict__ inst_desc,
+           uint32_t *__restrict__ bits)
+{
+    const int i = blockIdx.y;
+    const int64_t r0 = run_off[i], r1 = run_off[i + 1];
+    const int64_t r = r0 + 2 * (int64_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) + 1;
+    if (r >= r1) return;
+    const uint32_t len = runs[r];
+    if (len == 0) return;
+    const int32_t *d = inst_desc + i * CM3D_IN_WORDS;
+    const uint32_t W = (uint32_t)d[CM3D_IN_W], H = (uint32_t)d[CM3D_IN_H];
+    const int pitch = d[CM3D_IN_PITCH];
+    uint32_t *plane = bits + join64(d[CM3D_IN_BITS_LO], d[CM3D_IN_BITS_HI]);
+    const uint32_t s = run_start[r];
+    uint32_t e = s + len;                       // exclusive
+    if (e > W * H) e = W * H;                   // malformed input is flagged by k_rle_prefix
+    if (s >= e) return;
+    const uint32_t y0 = s / W, y1 = (e - 1) / W;
+    const unsigned lane = lane_id();
+    for (uint32_t y = y0; y <= y1; ++y) {
+        const uint32_t xa = (y == y0) ? s - y0 * W : 0u;
+        const uint32_t xb = (y == y1) ? (e - 1) - y1 * W + 1 : W;   // exclusive
+        const uint32_t wa = xa >> 5, wb = (xb - 1) >> 5;
+        for (uint32_t w = wa + lane; w <= wb; w += 32) {
+            const uint32_t lo = max(xa, w << 5) - (w << 5);
+            const uint32_t hi = min(xb, (w + 1) << 5) - (w << 5);   // 1..32
+            const uint32_t m = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+            atomicOr(plane + (size_t)y * pitch + w, m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ 3x3 erosion on bit planes
+__global__ void k_bbox_init(int32_t *__restrict__ bbox, int n_inst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_inst) {
+        bbox[4 * i + 0] = 0x7fffffff;
+        bbox[4 * i + 1] = 0x7fffffff;
+        bbox[4 * i + 2] = -1;
+        bbox[4 * i + 3] = -1;
+    }
+}
+
+// Horizontal 3-AND of one row word; pixels outside the image count as set (cv2's default
+// erosion border is +inf, so the border never lowers the minimum).
+__device__ __forceinline__ uint32_t hmin3(const uint32_t *__restrict__ row, int xw, int pitch, uint32_t tailmask)
+{
+    uint32_t c = __ldg(row + xw);
+    uint32_t l = xw > 0 ? __ldg(row + xw - 1) : 0xffffffffu;
+    uint32_t r = xw + 1 < pitch ? __ldg(row + xw + 1) : 0xffffffffu;
+    if (xw == pitch - 1) c |= ~tailmask;
+    if (xw + 1 == pitch - 1) r |= ~tailmask;
+    return c & ((c << 1) | (l >> 31)) & ((c >> 1) | (r << 31));
+}
+
+__global__ void __launch_bounds__(256)
+k_erode3x3(const uint32_t *__restrict__ bits_in, const int32_t *__restrict__ inst_desc,
+           uint32_t *__restrict__ bits_out, int32_t *__restrict__ bbox)
+{
+    const int i = blockIdx.y;
+    const int32_t *d = inst_desc + i * CM3D_IN_WORDS;
+    const int W = d[CM3D_IN_W], H = d[CM3D_IN_H], pitch = d[CM3D_IN_PITCH];
+    const int wd = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = wd < H * pitch;
+    uint32_t out = 0;
+    int y = 0, xw = 0;
+    if (live) {
+        y = wd / pitch;
+        xw = wd - y * pitch;
+        const int64_t off = join64(d[CM3D_IN_BITS_LO], d[CM3D_IN_BITS_HI]);
+        const uint32_t *plane = bits_in + off;
+        const uint32_t tailmask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xffffffffu;
+        out = hmin3(plane + (size_t)y * pitch, xw, pitch, tailmask);
+        if (y > 0) out &= hmin3(plane + (size_t)(y - 1) * pitch, xw, pitch, tailmask);
+        if (y + 1 < H) out &= hmin3(plane + (size_t)(y + 1) * pitch, xw, pitch, tailmask);
+        if (xw == pitch - 1) out &= tailmask;
+        bits_out[off + wd] = out;
+    }
+    // bounding box of the surviving pixels: warp-reduce, then 4 atomics per warp at most
+    int xmin = 0x7fffffff, ymin = 0x7fffffff, xmax = -1, ymax = -1;
+    if (out) {
+        xmin = xw * 32 + (__ffs(out) - 1);
+        xmax = xw * 32 + (31 - __clz(out));
+        ymin = ymax = y;
+    }
+    const unsigned full = 0xffffffffu;
+    if (__any_sync(full, out != 0)) {
+        xmin = __reduce_min_sync(full, xmin);
+        ymin = __reduce_min_sync(full, ymin);
+        xmax = __reduce_max_sync(full, xmax);
+        ymax = __reduce_max_sync(full, ymax);
+        if (lane_id() == 0) {
+            atomicMin(&bbox[4 * i + 0], xmin);
+            atomicMin(&bbox[4 * i + 1], ymin);
+            atomicMax(&bbox[4 * i + 2], xmax);
+            atomicMax(&bbox[4 * i + 3], ymax);
+        }
+    }
+}
+
+}  // namespace cm3d
+
+using namespace cm3d;
+
+extern "C" int cm3d_masks_pack_dense(const uint8_t *masks, const int64_t *src_off,
+                                     const int32_t *inst_desc, int n_inst, int max_words,
+                                     uint32_t *bits, void *stream)
+{
+    if (n_inst < 0 || max_words < 0) return CM3D_EINVAL;
+    if (n_inst == 0 || max_words == 0) return CM3D_OK;
+    if (!masks || !src_off || !inst_desc || !bits) return CM3D_EINVAL;
+    dim3 grid((max_words + 255) / 256, n_inst);
+    k_pack_dense<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, src_off, inst_desc, bits);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}
+
+extern "C" int cm3d_masks_fill_rle(const uint32_t *runs, const int64_t *run_off, uint32_t *run_start,
+                                   const int32_t *inst_desc, int n_inst, int max_runs, uint32_t *bits,
+                                   int32_t *errflags, void *stream)
+{
+    if (n_inst < 0 || max_runs < 0) return CM3D_EINVAL;
+    if (n_inst == 0) return CM3D_OK;
+    if (!run_off || !inst_desc || !bits || !errflags) return CM3D_EINVAL;
+    if (max_runs == 0) return CM3D_OK;
+    if (!runs || !run_start) return CM3D_EINVAL;
+    k_rle_prefix<<<n_inst, 256, 0, (cudaStream_t)stream>>>(runs, run_off, inst_desc, run_start, errflags);
+    CM3D_LAUNCH_CHECK();
+    const int one_runs = (max_runs + 1) / 2;          // 1-runs sit at odd positions
+    dim3 grid((one_runs + 7) / 8, n_inst);
+    k_rle_fill<<<grid, 256, 0, (cudaStream_t)stream>>>(runs, run_off, run_start, inst_desc, bits);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}
+
+extern "C" int cm3d_masks_erode3x3(const uint32_t *bits_in, const int32_t *inst_desc, int n_inst,
+                                   int max_words, uint32_t *bits_out, int32_t *bbox, void *stream)
+{
+    if (n_inst < 0 || max_words < 0) return CM3D_EINVAL;
+    if (n_inst == 0) return CM3D_OK;
+    if (!bits_in || !inst_desc || !bits_out || !bbox) return CM3D_EINVAL;
+    k_bbox_init<<<(n_inst + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bbox, n_inst);
+    CM3D_LAUNCH_CHECK();
+    if (max_words == 0) return CM3D_OK;
+    dim3 grid((max_words + 255) / 256, n_inst);
+    k_erode3x3<<<grid, 256, 0, (cudaStream_t)stream>>>(bits_in, inst_desc, bits_out, bbox);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}

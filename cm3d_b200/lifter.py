@@ -1,0 +1,247 @@
+"""`Lifter`: the host side of the lifting path - uploads a PackedBatch, launches the
+CUDA kernels through the C-ABI (include/cm3d_b200.h) and reads the labels back.
+
+It stands where the reference has the body of its frame loop
+(src/nuscenes/2d_to_3d.py:433-665; kitti:1066-1542; waymo:472-702): per frame,
+aggregate the sweeps, and per mask find the LiDAR points inside it and their
+medoid.  PyTorch is used for device memory, streams and pinned host buffers only.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .batch import ERR_WORDS, MEDOID_COLS, TILE, PackedBatch, pack_frames
+from .frames import FrameSpec, LiftResult
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+@dataclass
+class DeviceBatch:
+    pb: PackedBatch
+    raw: torch.Tensor
+    meta: torch.Tensor
+    mask: torch.Tensor
+    mask_off: torch.Tensor
+
+    def tab(self, name: str) -> torch.Tensor:
+        o = self.pb.off[name]
+        return self.meta[o:o + self.pb.off[name + "_n"]]
+
+
+@dataclass
+class DeviceOutputs:
+    db: DeviceBatch
+    out: torch.Tensor                 # packed int32 result block (see Lifter._out_layout)
+    layout: dict
+    seg_cap: int
+    seg_point_idx: torch.Tensor
+    seg_xyzw: torch.Tensor
+    xyzw: torch.Tensor
+    tile_cnt: torch.Tensor
+    tile_prefix: torch.Tensor
+    pix: Optional[torch.Tensor] = None
+    col_sums: Optional[torch.Tensor] = None
+    hits: Optional[torch.Tensor] = None
+    bits: Optional[torch.Tensor] = None
+    bbox: Optional[torch.Tensor] = None
+
+
+class Lifter:
+    """One per process / GPU.  All methods enqueue on the current torch CUDA stream."""
+
+    def __init__(self, device="cuda:0", seg_factor: float = 2.0):
+        if not torch.cuda.is_available():
+            raise N.Cm3dError("cm3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        self.seg_factor = float(seg_factor)
+        N.load()
+        self.launches = 0           # kernels launched by this object (bench.py reports it)
+
+    # ------------------------------------------------------------------ host -> device
+    def pack(self, frames: Sequence[FrameSpec]) -> PackedBatch:
+        return pack_frames(frames, pin=True)
+
+    def upload(self, pb: PackedBatch) -> DeviceBatch:
+        def up(name, arr):
+            t = pb.tensors.get(name)
+            src = t if t is not None else torch.from_numpy(arr)
+            if arr.dtype == np.uint32:          # torch has no uint32 arithmetic; move the bytes as int32
+                src = src.view(torch.int32) if t is not None else torch.from_numpy(arr.view(np.int32))
+            return src.to(self.device, non_blocking=True)
+        return DeviceBatch(pb, up("raw", pb.raw), up("meta", pb.meta), up("mask", pb.mask),
+                           up("mask_off", pb.mask_off))
+
+    # ------------------------------------------------------------------ launch sequence
+    @staticmethod
+    def _out_layout(F: int, I: int) -> dict:
+        lay, pos = {}, 0
+        for name, n in (("frame_n", F), ("seg_off", I + 1), ("item_off", I + 1), ("medoid_local", I),
+                        ("medoid_point_idx", I), ("centroid", 4 * I), ("errflags", ERR_WORDS)):
+            lay[name] = (pos, n)
+            pos += (n + 3) & ~3
+        lay["_words"] = pos
+        return lay
+
+    def run(self, db: DeviceBatch, seg_cap: Optional[int] = None, want_pix: bool = False,
+            want_col_sums: bool = False, do_medoid: bool = True) -> DeviceOutputs:
+        pb, dev = db.pb, self.device
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        F, I, T = pb.n_frames, pb.n_inst, pb.n_tiles
+        n_slots = max(T, 1) * TILE
+        if seg_cap is None:
+            seg_cap = int(self.seg_factor * pb.n_raw_points) + 1024
+        seg_cap = (int(seg_cap) + 3) & ~3
+        i32 = dict(dtype=torch.int32, device=dev)
+        lay = self._out_layout(F, I)
+        out = torch.zeros(lay["_words"], **i32)
+
+        def o(name):
+            a, n = lay[name]
+            return out[a:a + max(n, 1)]
+
+        # ---- masks -> eroded bit planes (+ bbox)
+        bits_raw = torch.empty(max(pb.bits_words, 1), **i32)
+        bits = torch.empty(max(pb.bits_words, 1), **i32)
+        bbox = torch.empty(max(I, 1) * 4, **i32)
+        inst_desc = db.tab("inst_desc")
+        if I:
+            if pb.masks_kind == "dense":
+                N.call("cm3d_masks_pack_dense", _ptr(db.mask), _ptr(db.mask_off), _ptr(inst_desc), I,
+                       pb.max_words, _ptr(bits_raw), st)
+                self.launches += 1
+            else:
+                bits_raw.zero_()
+                run_start = torch.empty(max(db.mask.numel(), 1), **i32)
+                N.call("cm3d_masks_fill_rle", _ptr(db.mask), _ptr(db.mask_off), _ptr(run_start), _ptr(inst_desc),
+                       I, pb.max_runs, _ptr(bits_raw), _ptr(o("errflags")), st)
+                self.launches += 3
+            N.call("cm3d_masks_erode3x3", _ptr(bits_raw), _ptr(inst_desc), I, pb.max_words, _ptr(bits),
+                   _ptr(bbox), st)
+            self.launches += 2
+
+        # ---- sweeps -> aggregated cloud
+        xyzw = torch.empty(4 * n_slots, dtype=torch.float32, device=dev)
+        tile_cnt = torch.empty(max(T, 1), **i32)
+        tile_prefix = torch.empty(max(T, 1), **i32)
+        N.call("cm3d_aggregate_sweeps", _ptr(db.raw), _ptr(db.tab("tile_sweep")), T, _ptr(db.tab("sweep_desc")),
+               _ptr(db.tab("frame_desc")), _ptr(db.tab("chains")), _ptr(xyzw), _ptr(tile_cnt), st)
+        self.launches += 1 if T else 0
+
+        # ---- projection + membership (count pass)
+        hits = torch.empty(n_slots, **i32)
+        tile_inst_cnt = torch.empty(max(pb.cnt_total, 1), dtype=torch.int16, device=dev)
+        tile_inst_base = torch.empty(max(pb.cnt_total, 1), **i32)
+        pix = torch.empty(16 * n_slots, **i32) if want_pix else None
+        N.call("cm3d_project_membership", _ptr(xyzw), _ptr(tile_cnt), _ptr(db.tab("tile_sweep")), T,
+               _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
+               _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
+               _ptr(hits), _ptr(tile_inst_cnt), _ptr(pix), st)
+        self.launches += 1 if T else 0
+
+        # ---- scans, ordered compaction + gather
+        medoid_best = torch.empty(max(I, 1), dtype=torch.int64, device=dev)
+        N.call("cm3d_scan_segments", _ptr(tile_cnt), _ptr(tile_inst_cnt), _ptr(db.tab("frame_desc")), F,
+               pb.max_inst_per_frame, I, _ptr(inst_desc), seg_cap, _ptr(tile_prefix), _ptr(o("frame_n")),
+               _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(o("item_off")), _ptr(medoid_best),
+               _ptr(o("errflags")), st)
+        self.launches += 2
+        seg_point_idx = torch.empty(seg_cap, **i32)
+        seg_xyzw = torch.empty(4 * seg_cap, dtype=torch.float32, device=dev)
+        N.call("cm3d_compact_segments", _ptr(xyzw), _ptr(tile_cnt), _ptr(tile_prefix), _ptr(db.tab("tile_sweep")),
+               T, _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
+               _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
+               _ptr(hits), _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(seg_point_idx), _ptr(seg_xyzw),
+               seg_cap, pb.max_inst_per_frame, _ptr(o("errflags")), st)
+        self.launches += 1 if T else 0
+
+        # ---- medoid
+        col_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if want_col_sums else None
+        if do_medoid and I:
+            max_items = seg_cap // MEDOID_COLS + I
+            N.call("cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), _ptr(seg_point_idx),
+                   _ptr(o("item_off")), I, max_items, _ptr(medoid_best), _ptr(col_sums), _ptr(o("medoid_local")),
+                   _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
+            self.launches += 2
+        return DeviceOutputs(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, xyzw, tile_cnt, tile_prefix,
+                             pix, col_sums, hits, bits, bbox)
+
+    # ------------------------------------------------------------------ device -> host
+    def fetch_labels(self, do: DeviceOutputs, pinned: Optional[torch.Tensor] = None) -> dict:
+        """D2H of the small per-instance result block (sizes, medoids, centroids, flags)."""
+        if pinned is not None:
+            pinned[:do.out.numel()].copy_(do.out, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            h = pinned[:do.out.numel()].numpy()
+        else:
+            h = do.out.cpu().numpy()
+        res = {}
+        for k, v in do.layout.items():
+            if k.startswith("_"):
+                continue
+            res[k] = h[v[0]:v[0] + v[1]]
+        res["centroid"] = res["centroid"].view(np.float32).reshape(-1, 4)
+        return res
+
+    def check_flags(self, labels: dict):
+        e = labels["errflags"]
+        if e[1]:
+            raise ValueError(f"instance {int(e[1]) - 1}: COCO run lengths do not cover the mask")
+        return int(e[0])            # members needed when the segment buffers were too small, else 0
+
+    def results(self, do: DeviceOutputs, labels: dict, with_points: bool = True, with_pix: bool = False) -> List[LiftResult]:
+        pb = do.db.pb
+        seg_off = labels["seg_off"].astype(np.int64)
+        total = int(seg_off[-1])
+        idx_all = do.seg_point_idx[:total].cpu().numpy() if with_points else None
+        aggr_all = tile_cnt = None
+        if with_points:
+            aggr_all = do.xyzw.view(4, -1).cpu().numpy()
+            tile_cnt = do.tile_cnt.cpu().numpy()
+        pix_all = do.pix.view(16, -1).cpu().numpy() if (with_pix and do.pix is not None) else None
+        fdesc = pb.table("frame_desc", 12)
+        out = []
+        for f in range(pb.n_frames):
+            i0, i1 = int(pb.frame_inst[f]), int(pb.frame_inst[f + 1])
+            offs = seg_off[i0:i1 + 1] - seg_off[i0]
+            r = LiftResult(
+                n_points=int(labels["frame_n"][f]),
+                seg_offsets=offs.astype(np.int32),
+                seg_point_idx=idx_all[seg_off[i0]:seg_off[i1]].copy() if with_points else None,
+                medoid_local=labels["medoid_local"][i0:i1].copy(),
+                medoid_point_idx=labels["medoid_point_idx"][i0:i1].copy(),
+                centroids=labels["centroid"][i0:i1, :3].copy())
+            if with_points:
+                tb, te = int(fdesc[f, 0]), int(fdesc[f, 1])
+                keep = (np.arange(TILE)[None, :] < tile_cnt[tb:te, None]).reshape(-1)
+                r.aggr_points = aggr_all[:, tb * TILE:te * TILE][:, keep]
+                if pix_all is not None:
+                    r.pix = pix_all[:len(pb.frame_vcam_cams[f]), tb * TILE:te * TILE][:, keep]
+            out.append(r)
+        return out
+
+    def lift_frames(self, frames: Sequence[FrameSpec], with_points: bool = True, with_pix: bool = False,
+                    want_col_sums: bool = False) -> List[LiftResult]:
+        """Synchronous convenience: pack, upload, run, read back; retries once with exact
+        segment capacity if the default guess was too small."""
+        pb = self.pack(frames)
+        db = self.upload(pb)
+        do = self.run(db, want_pix=with_pix, want_col_sums=want_col_sums)
+        labels = self.fetch_labels(do)
+        need = self.check_flags(labels)
+        if need:
+            do = self.run(db, seg_cap=need, want_pix=with_pix, want_col_sums=want_col_sums)
+            labels = self.fetch_labels(do)
+            if self.check_flags(labels):
+                raise N.Cm3dError("segment capacity retry failed")
+        res = self.results(do, labels, with_points, with_pix)
+        self.last = do
+        return res

@@ -1,0 +1,172 @@
+/* cm3d_b200 - C ABI of the B200-native 2D-mask -> 3D lifting path.
+ *
+ * The reference (meharkhurana03/cm3d) has no FFI: its hot path is the body of the
+ * frame loop / mask loop in src/{nuscenes,kitti,waymo}/2d_to_3d.py.  These entry
+ * points replace the regions the reference brackets with its own stopwatches
+ * ("io" tail, "points in mask", "medoid"), batched over many frames:
+ *
+ *   cm3d_masks_*            src/nuscenes/2d_to_3d.py:425-428 (RLE decode), :526-527,
+ *                           :543-544 (3x3 erosion, bool (W,H) view)
+ *   cm3d_aggregate_sweeps   src/nuscenes/2d_to_3d.py:437-465 (close-point removal,
+ *                           rotate/translate per sweep, hstack);
+ *                           src/kitti/2d_to_3d.py:1066-1083; src/waymo/2d_to_3d.py:472-486
+ *   cm3d_project_membership src/nuscenes/2d_to_3d.py:553-617 (clone, global->camera chain,
+ *                           view_points, bounds/depth test, floor, mask lookup);
+ *                           src/kitti/2d_to_3d.py:1238-1351; src/waymo/2d_to_3d.py:557-616
+ *   cm3d_scan_segments      (no reference counterpart: sizes of the boolean-index results)
+ *   cm3d_compact_segments   src/nuscenes/2d_to_3d.py:617-620 (track_points, gather)
+ *   cm3d_medoid             src/nuscenes/2d_to_3d.py:116-119,641-663 (cdist medoid, centroid)
+ *
+ * Conventions: every pointer is a DEVICE pointer; the caller (PyTorch) owns and
+ * sizes every buffer; nothing is allocated, nothing throws; all launches are
+ * asynchronous on `stream` (a cudaStream_t passed as void*); return 0 on success,
+ * a negative CM3D_E* code on bad arguments, or -(1000 + cudaError_t) when a launch
+ * fails.  One process per GPU.
+ *
+ * Descriptor tables are plain int32 arrays (floats stored by bit pattern) built on
+ * the host by cm3d_b200/batch.py; their layouts are fixed by the enums below.
+ *
+ * Geometry of a batch:
+ *   raw points   one float buffer; sweep s starts at a 4-float-aligned offset, is
+ *                npts*stride floats long and padded to a multiple of 4 floats.
+ *   tiles        every sweep is cut into tiles of CM3D_TILE raw points; tiles of a
+ *                frame are contiguous and in sweep order.  Tile t owns slots
+ *                [t*CM3D_TILE, t*CM3D_TILE + tile_cnt[t]) of the aggregated cloud
+ *                (survivors of the close-point filter, original order).  The index
+ *                of a point in the reference's `aggr_pc_points` is
+ *                tile_prefix[t] + (slot - t*CM3D_TILE).
+ *   instances    numbered frame-major over the batch; instance i owns
+ *                [seg_off[i], seg_off[i+1]) of seg_point_idx / seg_xyzw.
+ */
+#ifndef CM3D_B200_H
+#define CM3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM3D_ABI_VERSION 2
+#define CM3D_TILE 1024          /* points per tile: compaction / count granule */
+#define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
+#define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
+#define CM3D_MEDOID_COLS 256    /* columns of the distance matrix per medoid work item */
+
+enum {
+    CM3D_OK = 0,
+    CM3D_EINVAL = -1,           /* bad argument */
+    CM3D_ELIMIT = -2            /* a per-frame limit above is exceeded */
+};
+
+/* transform chain: CM3D_MAX_CHAIN ops of CM3D_OP_WORDS words: kind, 12 floats, 3 pad */
+enum { CM3D_OP_END = 0, CM3D_OP_T = 1, CM3D_OP_R = 2, CM3D_OP_A = 3 };
+#define CM3D_MAX_CHAIN 4
+#define CM3D_OP_WORDS 16
+#define CM3D_CHAIN_WORDS (CM3D_MAX_CHAIN * CM3D_OP_WORDS)
+
+/* sweep_desc[s][CM3D_SW_WORDS] */
+enum { CM3D_SW_RAW_LO = 0, CM3D_SW_RAW_HI, CM3D_SW_NPTS, CM3D_SW_STRIDE, CM3D_SW_FRAME,
+       CM3D_SW_TILE_BASE, CM3D_SW_CHAIN, CM3D_SW_FOURTH, CM3D_SW_WORDS };
+/* frame_desc[f][CM3D_FR_WORDS] */
+enum { CM3D_FR_TILE_BEGIN = 0, CM3D_FR_TILE_END, CM3D_FR_VCAM_BEGIN, CM3D_FR_NVCAMS,
+       CM3D_FR_INST_BEGIN, CM3D_FR_NINST, CM3D_FR_CLOSE_BITS, CM3D_FR_USE_CLOSE,
+       CM3D_FR_MIN_DEPTH_BITS, CM3D_FR_CNT_OFF, CM3D_FR_MIN_MEDOID_PTS, CM3D_FR_LIST_BEGIN,
+       CM3D_FR_WORDS };
+/* vcam_desc[v][CM3D_VC_WORDS]: one per (camera, mask size) of a frame */
+enum { CM3D_VC_CHAIN = 0, CM3D_VC_VIEWPAD = 1 /* 12 floats */, CM3D_VC_W = 13, CM3D_VC_H,
+       CM3D_VC_LIST_BEGIN /* into cam_inst_list, relative to the frame's LIST_BEGIN */,
+       CM3D_VC_LIST_COUNT, CM3D_VC_WORDS = 20 };
+/* inst_desc[i][CM3D_IN_WORDS] */
+enum { CM3D_IN_BITS_LO = 0, CM3D_IN_BITS_HI, CM3D_IN_W, CM3D_IN_H, CM3D_IN_PITCH, CM3D_IN_VCAM,
+       CM3D_IN_FRAME, CM3D_IN_LOCAL, CM3D_IN_WORDS };
+/* error flag words written by the kernels (errflags[CM3D_ERR_WORDS]) */
+enum { CM3D_ERR_SEG_OVERFLOW = 0 /* total members needed when > seg_cap */,
+       CM3D_ERR_RLE_SIZE = 1     /* 1 + first instance whose runs do not cover W*H */,
+       CM3D_ERR_WORDS = 4 };
+
+int cm3d_abi_version(void);
+const char *cm3d_error_string(int code);
+
+/* ---- masks: COCO runs or dense uint8 -> bit planes -> 3x3-eroded bit planes + bbox ------- */
+
+/* Dense (H,W) uint8 masks -> bit planes (bit x&31 of word y*pitch + x/32 = mask[y][x] != 0).
+ * src_off[i] = byte offset of instance i in `masks`. */
+int cm3d_masks_pack_dense(const uint8_t *masks, const int64_t *src_off, const int32_t *inst_desc,
+                          int n_inst, int max_words, uint32_t *bits, void *stream);
+
+/* COCO run lengths (alternating 0-run,1-run; row-major over the (H,W) image) -> bit planes.
+ * `bits` must be zero on entry.  run_start is scratch of the same length as runs. */
+int cm3d_masks_fill_rle(const uint32_t *runs, const int64_t *run_off, uint32_t *run_start,
+                        const int32_t *inst_desc, int n_inst, int max_runs, uint32_t *bits,
+                        int32_t *errflags, void *stream);
+
+/* cv2.erode(mask, ones(3,3)) on bit planes; bbox[i] = {xmin,ymin,xmax,ymax} of the eroded
+ * set bits ({INT_MAX,INT_MAX,-1,-1} if none). */
+int cm3d_masks_erode3x3(const uint32_t *bits_in, const int32_t *inst_desc, int n_inst, int max_words,
+                        uint32_t *bits_out, int32_t *bbox, void *stream);
+
+/* ---- sweeps -> aggregated cloud (tile-compacted SoA) ---------------------------------------- */
+
+/* xyzw: 4 arrays of n_slots floats (x | y | z | 4th row), n_slots = n_tiles*CM3D_TILE.
+ * tile_sweep[t] = sweep the tile belongs to. */
+int cm3d_aggregate_sweeps(const float *raw, const int32_t *tile_sweep, int n_tiles,
+                          const int32_t *sweep_desc, const int32_t *frame_desc,
+                          const uint32_t *chains, float *xyzw, int32_t *tile_cnt, void *stream);
+
+/* ---- projection + mask membership ------------------------------------------------------------- */
+
+/* hits[slot]: up to four frame-local instance ids (+1) in ascending order, one per byte,
+ * 0 = none; byte 3 == 255 means "more than four, recompute".
+ * tile_inst_cnt[cnt_off(f) + j*ntiles(f) + (t - tile_begin(f))] = members of instance j in tile t.
+ * pix (optional, may be NULL): pix[v*n_slots + slot] = fx | fy<<16 of the point in the
+ * frame's v-th vcam, or -1 when it fails the depth / image-bounds test. */
+int cm3d_project_membership(const float *xyzw, const int32_t *tile_cnt, const int32_t *tile_sweep,
+                            int n_tiles, const int32_t *sweep_desc, const int32_t *frame_desc,
+                            const int32_t *vcam_desc, const int32_t *cam_inst_list,
+                            const int32_t *inst_desc, const int32_t *inst_bbox,
+                            const uint32_t *chains, const uint32_t *bits, uint32_t *hits,
+                            uint16_t *tile_inst_cnt, int32_t *pix, void *stream);
+
+/* Scans.  tile_prefix[t] = index in the frame's aggr_pc_points of tile t's first point;
+ * frame_n[f] = N of frame f; tile_inst_base = exclusive prefix of tile_inst_cnt over the
+ * frame's tiles (same layout, int32); seg_off[n_inst_total+1] = exclusive prefix of the
+ * per-instance member counts; item_off[n_inst_total+1] = exclusive prefix of the medoid
+ * work items (ceil(M/CM3D_MEDOID_COLS) for instances with M >= the frame's minimum, else 0);
+ * medoid_best is reset.  Sets errflags[CM3D_ERR_SEG_OVERFLOW] when seg_off[end] > seg_cap. */
+int cm3d_scan_segments(const int32_t *tile_cnt, const uint16_t *tile_inst_cnt,
+                       const int32_t *frame_desc, int n_frames, int max_inst_per_frame,
+                       int n_inst_total, const int32_t *inst_desc, int64_t seg_cap,
+                       int32_t *tile_prefix, int32_t *frame_n, int32_t *tile_inst_base,
+                       int32_t *seg_off, int32_t *item_off, unsigned long long *medoid_best,
+                       int32_t *errflags, void *stream);
+
+/* Ordered (ascending point index) per-instance index lists + gathered points.
+ * seg_xyzw: 4 arrays of seg_cap floats.  Does nothing when the overflow flag is set. */
+int cm3d_compact_segments(const float *xyzw, const int32_t *tile_cnt, const int32_t *tile_prefix,
+                          const int32_t *tile_sweep, int n_tiles, const int32_t *sweep_desc,
+                          const int32_t *frame_desc, const int32_t *vcam_desc,
+                          const int32_t *cam_inst_list, const int32_t *inst_desc,
+                          const int32_t *inst_bbox, const uint32_t *chains, const uint32_t *bits,
+                          const uint32_t *hits, const int32_t *tile_inst_base,
+                          const int32_t *seg_off, int32_t *seg_point_idx, float *seg_xyzw,
+                          int64_t seg_cap, int max_inst_per_frame, const int32_t *errflags,
+                          void *stream);
+
+/* ---- medoid ---------------------------------------------------------------------------------- */
+
+/* medoid_local[i] = argmin_j sum_k ||p_k - p_j|| with torch.cdist / sum(axis=0) arithmetic
+ * (-1 if the instance has fewer than its frame's minimum points); medoid_point_idx = that
+ * point's index in aggr_pc_points; centroid[4*i..] = its x,y,z,4th row (NaN when absent).
+ * col_sums (optional, seg_cap floats) receives every column sum.  max_items bounds the grid:
+ * it must be >= item_off[n_inst_total] (seg_cap/CM3D_MEDOID_COLS + n_inst_total always is). */
+int cm3d_medoid(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off,
+                const int32_t *seg_point_idx, const int32_t *item_off, int n_inst_total,
+                int max_items, unsigned long long *medoid_best, float *col_sums,
+                int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
+                const int32_t *errflags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CM3D_B200_H */

@@ -1,0 +1,156 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the golden fixtures made with the
+reference's own pcd.py / kitti_utils (tests/golden) and against the C oracle on seeded frames.
+
+Bars: aggregated cloud, pixel indices, per-instance point index lists, medoid index: BIT-EXACT.
+Centroids are copies of input points, so they are bit-exact too (tolerance 0)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lifter():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from cm3d_b200.lifter import Lifter
+    return Lifter("cuda:0")
+
+
+def _check_against_golden(frame, d, r, vcams):
+    aggr = d["aggr"]
+    if frame.dataset == "kitti":
+        aggr = aggr.T                                   # golden keeps the reference's (N,3) rows
+    n = int(d["n_points"])
+    assert r.n_points == n
+    rows = aggr.shape[0]
+    assert np.array_equal(r.aggr_points[:rows].view(np.uint32), np.ascontiguousarray(aggr).view(np.uint32))
+    # projected pixel indices, per camera that has an instance
+    for c in d["pix_cams"]:
+        v = [k for k, key in enumerate(vcams) if key[0] == int(c)][0]
+        code = r.pix[v]
+        sel = np.flatnonzero(code >= 0)
+        assert np.array_equal(sel, d[f"pix_{c}_idx"])
+        assert np.array_equal(code[sel] & 0xFFFF, d[f"pix_{c}_fx"].astype(np.int64))
+        assert np.array_equal(code[sel] >> 16, d[f"pix_{c}_fy"].astype(np.int64))
+    assert np.array_equal(r.seg_offsets.astype(np.int64), d["seg_offsets"])
+    assert np.array_equal(r.seg_point_idx, d["seg_point_idx"])
+    assert np.array_equal(r.medoid_local, d["medoid_local"])
+    assert np.array_equal(r.medoid_point_idx, d["medoid_point_idx"])
+    has = d["medoid_local"] >= 0
+    assert np.array_equal(r.centroids[has].view(np.uint32), d["centroids"][has].view(np.uint32))
+    assert np.all(np.isnan(r.centroids[~has]))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_single(lifter, name):
+    frame, d = load_golden(name)
+    r = lifter.lift_frames([frame], with_points=True, with_pix=True)[0]
+    _check_against_golden(frame, d, r, lifter.last.db.pb.frame_vcam_cams[0])
+
+
+def test_golden_mixed_batch(lifter):
+    """All fixtures (three datasets, dense and RLE masks) in one launch sequence."""
+    pairs = [load_golden(n) for n in GOLDEN]
+    res = lifter.lift_frames([p[0] for p in pairs] * 2, with_points=True, with_pix=True)
+    for k, r in enumerate(res):
+        frame, d = pairs[k % len(pairs)]
+        _check_against_golden(frame, d, r, lifter.last.db.pb.frame_vcam_cams[k])
+
+
+def test_dense_and_rle_masks_agree(lifter):
+    from cm3d_b200.synthetic import dense_to_rle
+    frame, d = load_golden("nusc_small")
+    assert isinstance(frame.masks, np.ndarray)
+    a = lifter.lift_frames([frame])[0]
+    frame.masks = dense_to_rle(frame.masks)
+    b = lifter.lift_frames([frame])[0]
+    assert np.array_equal(a.seg_point_idx, b.seg_point_idx)
+    assert np.array_equal(a.medoid_local, b.medoid_local)
+
+
+@pytest.mark.parametrize("cfg,scale,mask_div", [("c1", 1.0, 1), ("c2", 0.25, 1), ("c3", 0.5, 1), ("c4", 0.25, 1)])
+def test_against_c_oracle(lifter, cfg, scale, mask_div):
+    from cm3d_b200 import synthetic as S
+    from oracle import c_oracle as CO
+    frames = [S.make_frame(cfg, i, scale=scale, mask_div=mask_div) for i in range(2)]
+    res = lifter.lift_frames(frames, with_points=True, want_col_sums=True)
+    sums = lifter.last.col_sums.cpu().numpy()
+    seg_off = lifter.last.out.cpu().numpy()
+    for fi, (f, r) in enumerate(zip(frames, res)):
+        o = CO.lift_frame_c(f, record_pix=False)
+        aggr = o["aggr"].T if f.dataset == "kitti" else o["aggr"]
+        assert r.n_points == o["n_points"]
+        assert np.array_equal(r.aggr_points[:aggr.shape[0]].view(np.uint32), np.ascontiguousarray(aggr).view(np.uint32))
+        for i in range(f.n_instances):
+            assert np.array_equal(r.instance_points(i), o["idx"][i]), (cfg, fi, i)
+        assert np.array_equal(r.medoid_local, o["medoid_local"])
+        assert np.array_equal(r.medoid_point_idx, o["medoid_point_idx"])
+
+
+def test_column_sums_bit_exact(lifter):
+    """Every column sum of the distance matrix equals the C oracle's, bit for bit, for a range of
+    segment sizes (M <= 25 direct formula, M % 32 tails, M < 8)."""
+    from cm3d_b200 import synthetic as S
+    from oracle import c_oracle as CO
+    f = S.make_frame("c1", 3)
+    r = lifter.lift_frames([f], with_points=True, want_col_sums=True)[0]
+    sums = lifter.last.col_sums.cpu().numpy()
+    for i in range(f.n_instances):
+        idx = r.instance_points(i)
+        if idx.size == 0:
+            continue
+        j, ref = CO.medoid(r.aggr_points[:3][:, idx], want_sums=True)
+        got = sums[r.seg_offsets[i]:r.seg_offsets[i + 1]]
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), i
+        assert r.medoid_local[i] == j
+
+
+def test_small_segments_all_sizes(lifter):
+    """Medoid for M = 1..70 (covers M<8, M<=25, 25<M, every M%32 tail) via hand-made masks."""
+    from cm3d_b200 import synthetic as S
+    from oracle import c_oracle as CO
+    f = S.make_nuscenes_frame(4242, n_sweeps=1, pts_per_sweep=20000, n_inst=12, mask_div=2)
+    r = lifter.lift_frames([f], with_points=True, want_col_sums=True)[0]
+    sums = lifter.last.col_sums.cpu().numpy()
+    seen = set()
+    for i in range(f.n_instances):
+        idx = r.instance_points(i)
+        for m in range(1, min(idx.size, 70) + 1):
+            seen.add(m)
+    # run the medoid kernel on truncated segments by building 1-frame batches is heavy; instead
+    # check the kernel on synthetic segments through the C-ABI directly
+    import torch, ctypes
+    from cm3d_b200 import _native as N
+    rng = np.random.default_rng(0)
+    sizes = list(range(1, 71)) + [95, 96, 97, 255, 256, 257, 1023, 1025]
+    pts = [(rng.normal(0, 3, (3, m)) + np.array([[1200.0], [950.0], [1.0]])).astype(np.float32) for m in sizes]
+    seg_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    cap = int(seg_off[-1] + 3) & ~3
+    xyzw = np.zeros((4, cap), np.float32)
+    xyzw[:3, :seg_off[-1]] = np.concatenate(pts, 1)
+    items = [-(-m // 256) for m in sizes]
+    item_off = np.concatenate([[0], np.cumsum(items)]).astype(np.int32)
+    dev = "cuda:0"
+    t = lambda a: torch.from_numpy(a).to(dev)
+    d_xyzw, d_off, d_item = t(xyzw.reshape(-1)), t(seg_off), t(item_off)
+    d_idx = torch.arange(cap, dtype=torch.int32, device=dev)
+    n = len(sizes)
+    best = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    col = torch.zeros(cap, dtype=torch.float32, device=dev)
+    ml = torch.zeros(n, dtype=torch.int32, device=dev)
+    mp = torch.zeros(n, dtype=torch.int32, device=dev)
+    cen = torch.zeros(4 * n, dtype=torch.float32, device=dev)
+    err = torch.zeros(4, dtype=torch.int32, device=dev)
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), n, int(item_off[-1]) + 3, p(best), p(col),
+           p(ml), p(mp), p(cen), p(err), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    col, ml = col.cpu().numpy(), ml.cpu().numpy()
+    for k, m in enumerate(sizes):
+        j, ref = CO.medoid(pts[k], want_sums=True)
+        got = col[seg_off[k]:seg_off[k + 1]]
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), m
+        assert ml[k] == j, m
