@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the 2D-mask -> 3D lifting path (BASELINE.json metric: pseudo-label frames/s on
+nuScenes-shaped 10-sweep x 6-camera frames, plus achieved HBM GB/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A step is one pass of the whole hot path (mask decode+erosion, sweep aggregation, projection,
+membership, ordered gather, medoid) over one batch of B synthetic C2 frames per GPU.
+  value  frames/s with the packed batch already resident in HBM (CUDA events, max over ranks)
+  e2e    frames/s through the public API (Lifter.upload/run/fetch_labels) from pinned HOST
+         buffers, H2D and D2H inside the timed region
+Under torchrun (N>1) every rank lifts its own frames (sharded by sample index, no collective
+on the data path); NCCL is only used for the barrier and the max-over-ranks of the timings.
+`--impl reference` times the reference's own CPU algorithm (oracle/ref_lift.py: the restated
+per-frame body with the same torch calls) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pseudo_label_frames_per_s"
+UNIT = "frames/s"
+WORKLOAD = "C2: nuScenes-shaped 10 sweeps x 34,720 pts (~347k pts) x 6 cams 1024x576 masks x 50 instances per frame"
+
+
+def _gen_frame(index):
+    from cm3d_b200 import synthetic as S
+    return S.make_frame("c5", index, dense_masks=False)      # C5 = independent C2-shaped frames
+
+
+def make_frames(first, count, workers):
+    idx = list(range(first, first + count))
+    if workers <= 1 or count <= 2:
+        return [_gen_frame(i) for i in idx]
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(workers) as pool:
+        return pool.map(_gen_frame, idx)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(frames, threads):
+    """The reference's per-frame body (oracle/ref_lift.py, torch CPU) over `frames`; seconds."""
+    import torch
+    from oracle import ref_lift as RL
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    for f in frames:
+        RL.lift_frame(f, record_pix=False)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    nf = max(1, args.ref_frames)
+    frames = make_frames(0, nf, 1)
+    for _ in range(args.warmup):
+        cpu_reference_run(frames[:1], threads)
+    times = [cpu_reference_run(frames, threads) for _ in range(args.steps)]
+    total = sum(times)
+    v = nf * args.steps / total
+    sample = f"{nf} C2 frame(s) per step x {args.steps} steps, oracle/ref_lift.py (torch {torch.__version__} CPU)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": nf, "mask_input": "COCO run lengths"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, world, local_rank):
+    # frames first (spawned workers), CUDA afterwards
+    workers = max(1, min(args.workers or (os.cpu_count() or 1) // max(world, 1), 16))
+    t_gen = time.perf_counter()
+    frames = make_frames(rank * args.batch, args.batch, workers)
+    t_gen = time.perf_counter() - t_gen
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from cm3d_b200.lifter import Lifter
+
+    lifter = Lifter(dev)
+    pb = lifter.pack(frames)
+    db = lifter.upload(pb)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- find the segment capacity once (exact), then warm up
+    do = lifter.run(db)
+    labels = lifter.fetch_labels(do)
+    need = lifter.check_flags(labels)
+    seg_total = int(labels["seg_off"][-1])
+    seg_cap = max(need, seg_total) + 4096
+    n_points = int(labels["frame_n"].sum())
+    items = int(labels["item_off"][-1])
+    so = labels["seg_off"].astype(np.int64)
+    m = np.diff(so)
+    pairs = float((m.astype(np.float64) ** 2).sum())
+    del do
+    for _ in range(max(args.warmup, 3)):
+        lifter.run(db, seg_cap=seg_cap)
+    barrier()
+
+    # ---- device-resident timed region (CUDA events on the launch stream, per-kernel events inside)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lifter.timing = {}
+    lifter.launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        do = lifter.run(db, seg_cap=seg_cap)
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = lifter.launches
+    timing = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in lifter.timing.items()}
+    lifter.timing = None
+    final = lifter.fetch_labels(do)
+    assert lifter.check_flags(final) == 0
+
+    # ---- end to end: pinned host buffers -> H2D -> kernels -> D2H of the labels, every step
+    pinned_out = torch.empty(do.out.numel(), dtype=torch.int32, pin_memory=True)
+    for _ in range(2):
+        lifter.fetch_labels(lifter.run(lifter.upload(pb), seg_cap=seg_cap), pinned_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d = lifter.upload(pb)
+        o = lifter.run(d, seg_cap=seg_cap)
+        lab = lifter.fetch_labels(o, pinned_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert np.array_equal(lab["medoid_point_idx"], final["medoid_point_idx"])
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        total_frames = args.batch * world * args.steps
+        value = total_frames / (dev_ms * 1e-3)
+        e2e = total_frames / (e2e_ms * 1e-3)
+        peak, peak_src = measured_peak()
+        raw_bytes = int(pb.raw.nbytes)
+        algo = {   # algorithmic bytes per launch (DESIGN.md "Kernels and rooflines")
+            "aggregate": raw_bytes + 16 * n_points,
+            "project_count": 16 * n_points,
+            "compact": 4 * n_points + 36 * seg_total,
+            "masks_rle": int(pb.mask.nbytes) + 4 * pb.bits_words,
+            "masks_erode": 8 * pb.bits_words,
+        }
+        kern = {}
+        for k, ms in timing.items():
+            kern[k] = {"ms": ms, "share": ms * args.steps / dev_ms}
+            if k in algo:
+                kern[k]["algo_bytes"] = algo[k]
+                kern[k]["gbps"] = algo[k] / (ms * 1e-3) / 1e9
+        hbm_k = max((k for k in kern if k in ("aggregate", "project_count", "compact")), key=lambda k: kern[k]["ms"])
+        roof = {"kernel": hbm_k, "bound": "hbm", "achieved": kern[hbm_k]["gbps"], "peak": peak, "unit": "GB/s",
+                "frac": kern[hbm_k]["gbps"] / peak, "traffic": None, "peak_source": peak_src}
+        if "medoid" in timing:
+            kern["medoid"]["pair_distances"] = pairs
+            kern["medoid"]["gpairs_per_s"] = pairs / (timing["medoid"] * 1e-3) / 1e9
+            kern["medoid"]["bound"] = "fp32 ALU (O(sum M^2) pair distances, reads only sum M points)"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": args.batch, "mask_input": "COCO run lengths",
+                       "points_per_step": n_points, "member_points_per_step": seg_total,
+                       "l2": f"inputs per step {pb.h2d_bytes / 1e6:.0f} MB + {4 * 5 * pb.n_tiles * 1024 / 1e6:.0f} MB "
+                             f"intermediates > 126 MB L2, no explicit flush",
+                       "parallelism": f"frames sharded by sample index, {world} process(es), no collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pb.h2d_bytes * world,
+                    "d2h_bytes_per_step": int(do.out.numel() * 4) * world, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "kernels": kern,
+            "gen_seconds": round(t_gen, 1),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            nf = max(1, args.ref_frames)
+            from cm3d_b200 import synthetic as S
+            cpu_reference_run([S.make_frame("c1", 0, scale=0.25)], threads)      # spin up the torch thread pool
+            secs = cpu_reference_run(frames[:nf], threads)
+            line["cpu_baseline"] = {"value": nf / secs, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{nf} of this step's C2 frames through oracle/ref_lift.py "
+                                              f"(torch {torch.__version__} CPU, {threads} threads), after a small warm-up frame"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-frames", type=int, default=2, help="frames of the CPU sample")
+    ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        args.ref_frames = 1 if args.ref_frames == 2 else args.ref_frames
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

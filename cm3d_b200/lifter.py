@@ -65,6 +65,18 @@ class Lifter:
         self.seg_factor = float(seg_factor)
         N.load()
         self.launches = 0           # kernels launched by this object (bench.py reports it)
+        self.timing = None          # dict label -> [(start_event, end_event)] when bench.py profiles
+
+    def _call(self, label: str, name: str, *args):
+        """One C-ABI call; with `self.timing` set, bracketed by CUDA events on the launch stream."""
+        if self.timing is None:
+            N.call(name, *args)
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        N.call(name, *args)
+        b.record()
+        self.timing.setdefault(label, []).append((a, b))
 
     # ------------------------------------------------------------------ host -> device
     def pack(self, frames: Sequence[FrameSpec]) -> PackedBatch:
@@ -115,16 +127,16 @@ class Lifter:
         inst_desc = db.tab("inst_desc")
         if I:
             if pb.masks_kind == "dense":
-                N.call("cm3d_masks_pack_dense", _ptr(db.mask), _ptr(db.mask_off), _ptr(inst_desc), I,
+                self._call("masks_pack", "cm3d_masks_pack_dense", _ptr(db.mask), _ptr(db.mask_off), _ptr(inst_desc), I,
                        pb.max_words, _ptr(bits_raw), st)
                 self.launches += 1
             else:
                 bits_raw.zero_()
                 run_start = torch.empty(max(db.mask.numel(), 1), **i32)
-                N.call("cm3d_masks_fill_rle", _ptr(db.mask), _ptr(db.mask_off), _ptr(run_start), _ptr(inst_desc),
+                self._call("masks_rle", "cm3d_masks_fill_rle", _ptr(db.mask), _ptr(db.mask_off), _ptr(run_start), _ptr(inst_desc),
                        I, pb.max_runs, _ptr(bits_raw), _ptr(o("errflags")), st)
                 self.launches += 3
-            N.call("cm3d_masks_erode3x3", _ptr(bits_raw), _ptr(inst_desc), I, pb.max_words, _ptr(bits),
+            self._call("masks_erode", "cm3d_masks_erode3x3", _ptr(bits_raw), _ptr(inst_desc), I, pb.max_words, _ptr(bits),
                    _ptr(bbox), st)
             self.launches += 2
 
@@ -132,7 +144,7 @@ class Lifter:
         xyzw = torch.empty(4 * n_slots, dtype=torch.float32, device=dev)
         tile_cnt = torch.empty(max(T, 1), **i32)
         tile_prefix = torch.empty(max(T, 1), **i32)
-        N.call("cm3d_aggregate_sweeps", _ptr(db.raw), _ptr(db.tab("tile_sweep")), T, _ptr(db.tab("sweep_desc")),
+        self._call("aggregate", "cm3d_aggregate_sweeps", _ptr(db.raw), _ptr(db.tab("tile_sweep")), T, _ptr(db.tab("sweep_desc")),
                _ptr(db.tab("frame_desc")), _ptr(db.tab("chains")), _ptr(xyzw), _ptr(tile_cnt), st)
         self.launches += 1 if T else 0
 
@@ -141,7 +153,7 @@ class Lifter:
         tile_inst_cnt = torch.empty(max(pb.cnt_total, 1), dtype=torch.int16, device=dev)
         tile_inst_base = torch.empty(max(pb.cnt_total, 1), **i32)
         pix = torch.empty(16 * n_slots, **i32) if want_pix else None
-        N.call("cm3d_project_membership", _ptr(xyzw), _ptr(tile_cnt), _ptr(db.tab("tile_sweep")), T,
+        self._call("project_count", "cm3d_project_membership", _ptr(xyzw), _ptr(tile_cnt), _ptr(db.tab("tile_sweep")), T,
                _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
                _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
                _ptr(hits), _ptr(tile_inst_cnt), _ptr(pix), st)
@@ -149,14 +161,14 @@ class Lifter:
 
         # ---- scans, ordered compaction + gather
         medoid_best = torch.empty(max(I, 1), dtype=torch.int64, device=dev)
-        N.call("cm3d_scan_segments", _ptr(tile_cnt), _ptr(tile_inst_cnt), _ptr(db.tab("frame_desc")), F,
+        self._call("scan", "cm3d_scan_segments", _ptr(tile_cnt), _ptr(tile_inst_cnt), _ptr(db.tab("frame_desc")), F,
                pb.max_inst_per_frame, I, _ptr(inst_desc), seg_cap, _ptr(tile_prefix), _ptr(o("frame_n")),
                _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(o("item_off")), _ptr(medoid_best),
                _ptr(o("errflags")), st)
         self.launches += 2
         seg_point_idx = torch.empty(seg_cap, **i32)
         seg_xyzw = torch.empty(4 * seg_cap, dtype=torch.float32, device=dev)
-        N.call("cm3d_compact_segments", _ptr(xyzw), _ptr(tile_cnt), _ptr(tile_prefix), _ptr(db.tab("tile_sweep")),
+        self._call("compact", "cm3d_compact_segments", _ptr(xyzw), _ptr(tile_cnt), _ptr(tile_prefix), _ptr(db.tab("tile_sweep")),
                T, _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
                _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
                _ptr(hits), _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(seg_point_idx), _ptr(seg_xyzw),
@@ -167,7 +179,7 @@ class Lifter:
         col_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if want_col_sums else None
         if do_medoid and I:
             max_items = seg_cap // MEDOID_COLS + I
-            N.call("cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), _ptr(seg_point_idx),
+            self._call("medoid", "cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), _ptr(seg_point_idx),
                    _ptr(o("item_off")), I, max_items, _ptr(medoid_best), _ptr(col_sums), _ptr(o("medoid_local")),
                    _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
             self.launches += 2
