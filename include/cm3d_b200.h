@@ -166,6 +166,10 @@ int cm3d_medoid(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off,
                 int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
                 const int32_t *errflags, void *stream);
 
+/* Self-test: counts (adds to *mismatches) the floats in [2^-101, FLT_MAX] U {0} on which the
+ * medoid kernel's branch-free square root differs from IEEE sqrt.rn.f32.  Must stay 0. */
+int cm3d_selftest_sqrt(unsigned long long *mismatches, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -154,3 +154,15 @@ def test_small_segments_all_sizes(lifter):
         got = col[seg_off[k]:seg_off[k + 1]]
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), m
         assert ml[k] == j, m
+
+
+def test_fast_sqrt_exhaustive(lifter):
+    """The medoid kernel's branch-free sqrt equals IEEE sqrt.rn on every float of its domain."""
+    import ctypes
+    import torch
+    from cm3d_b200 import _native as N
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+    N.call("cm3d_selftest_sqrt", ctypes.c_void_p(bad.data_ptr()),
+           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
