@@ -105,9 +105,11 @@ k_aggregate(const float *__restrict__ raw, const int32_t *__restrict__ tile_swee
 // ------------------------------------------------------------------------------------------
 // Per-frame tables staged in shared memory by the membership kernels.
 struct VcamS {
-    uint32_t chain[CM3D_CHAIN_WORDS];
-    float vp[12];
-    float wlim, hlim;      // float(W-1), float(H-1)
+    float4 m[CM3D_MAX_CHAIN][3];   // 12 constants per op (16-byte aligned: three broadcast LDS.128)
+    float4 vp[3];                  // rows 0..2 of view_points' 4x4 viewpad
+    int kind[CM3D_MAX_CHAIN];
+    float wlim, hlim;              // float(W-1), float(H-1): the reference's strict upper bounds
+    float wcap, hcap;              // float(W), float(H): conservative reject bounds (see project_n)
     int list_begin, list_count;
 };
 struct InstS {
@@ -141,15 +143,18 @@ __device__ __forceinline__ void load_frame_tables(FrameTables &ft, const int32_t
     }
     for (int k = threadIdx.x; k < nv * CM3D_CHAIN_WORDS; k += blockDim.x) {
         const int v = k / CM3D_CHAIN_WORDS, wd = k - v * CM3D_CHAIN_WORDS;
+        const int op = wd / CM3D_OP_WORDS, q = wd - op * CM3D_OP_WORDS;
         const int32_t *vd = vcam_desc + (size_t)(v0 + v) * CM3D_VC_WORDS;
-        ft.vcam[v].chain[wd] = chains[(size_t)vd[CM3D_VC_CHAIN] * CM3D_CHAIN_WORDS + wd];
+        const uint32_t val = chains[(size_t)vd[CM3D_VC_CHAIN] * CM3D_CHAIN_WORDS + wd];
+        if (q == 0) ft.vcam[v].kind[op] = (int)val;
+        else if (q <= 12) reinterpret_cast<float *>(ft.vcam[v].m[op])[q - 1] = __uint_as_float(val);
     }
     for (int k = threadIdx.x; k < nv * 16; k += blockDim.x) {
         const int v = k >> 4, wd = k & 15;
         const int32_t *vd = vcam_desc + (size_t)(v0 + v) * CM3D_VC_WORDS;
-        if (wd < 12) ft.vcam[v].vp[wd] = __int_as_float(vd[CM3D_VC_VIEWPAD + wd]);
-        else if (wd == 12) ft.vcam[v].wlim = (float)(vd[CM3D_VC_W] - 1);
-        else if (wd == 13) ft.vcam[v].hlim = (float)(vd[CM3D_VC_H] - 1);
+        if (wd < 12) reinterpret_cast<float *>(ft.vcam[v].vp)[wd] = __int_as_float(vd[CM3D_VC_VIEWPAD + wd]);
+        else if (wd == 12) { ft.vcam[v].wlim = (float)(vd[CM3D_VC_W] - 1); ft.vcam[v].wcap = (float)vd[CM3D_VC_W]; }
+        else if (wd == 13) { ft.vcam[v].hlim = (float)(vd[CM3D_VC_H] - 1); ft.vcam[v].hcap = (float)vd[CM3D_VC_H]; }
         else if (wd == 14) ft.vcam[v].list_begin = vd[CM3D_VC_LIST_BEGIN];
         else ft.vcam[v].list_count = vd[CM3D_VC_LIST_COUNT];
     }
@@ -166,42 +171,90 @@ __device__ __forceinline__ void load_frame_tables(FrameTables &ft, const int32_t
     }
 }
 
-// Project one point into vcam `vc`; returns fx | fy<<16, or -1 when it fails the reference's
-// `depths > min_dist, 0 < u < W-1, 0 < v < H-1` test (nuscenes:597-603).
-__device__ __forceinline__ int32_t project_point(const VcamS &vc, float min_depth, float x, float y, float z)
+// Project NP points into vcam `vc`; code = fx | fy<<16, or -1 when the point fails the
+// reference's `depths > min_dist, 0 < u < W-1, 0 < v < H-1` test (nuscenes:597-603).
+// The op kinds are uniform over the block, so the constants are loaded once per op and
+// applied to all NP points.  Before the two IEEE divisions a division-free test throws out
+// points that cannot pass: for r2 > 0, r0 <= 0 gives u <= 0, and r0 >= fl(r2*W) gives a true
+// quotient >= W(1-2^-24) > W-1/2, whose rounding is >= W-1; both fail the strict bounds, so the
+// filter never changes a result (same for v).
+template <int NP>
+__device__ __forceinline__ void project_n(const VcamS &vc, float min_depth, const float (&px)[NP],
+                                          const float (&py)[NP], const float (&pz)[NP], int32_t (&code)[NP])
 {
-    apply_chain(vc.chain, x, y, z);
-    if (!(z > min_depth)) return -1;
-    const float *m = vc.vp;
-    const float r0 = __fmaf_rn(m[3], 1.0f, __fmaf_rn(m[2], z, __fmaf_rn(m[1], y, __fmul_rn(m[0], x))));
-    const float r1 = __fmaf_rn(m[7], 1.0f, __fmaf_rn(m[6], z, __fmaf_rn(m[5], y, __fmul_rn(m[4], x))));
-    const float r2 = __fmaf_rn(m[11], 1.0f, __fmaf_rn(m[10], z, __fmaf_rn(m[9], y, __fmul_rn(m[8], x))));
-    const float u = __fdiv_rn(r0, r2), v = __fdiv_rn(r1, r2);
-    if (u > 0.0f && u < vc.wlim && v > 0.0f && v < vc.hlim)
-        return (int32_t)floorf(u) | ((int32_t)floorf(v) << 16);
-    return -1;
+    float x[NP], y[NP], z[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { x[p] = px[p]; y[p] = py[p]; z[p] = pz[p]; }
+#pragma unroll
+    for (int k = 0; k < CM3D_MAX_CHAIN; ++k) {
+        const int kind = vc.kind[k];
+        if (kind == CM3D_OP_END) break;
+        const float4 a = vc.m[k][0], b = vc.m[k][1], c = vc.m[k][2];
+        if (kind == CM3D_OP_T) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                x[p] = __fadd_rn(x[p], a.x); y[p] = __fadd_rn(y[p], a.y); z[p] = __fadd_rn(z[p], a.z);
+            }
+        } else if (kind == CM3D_OP_R) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float u = x[p], v = y[p], w = z[p];
+                x[p] = __fmaf_rn(a.z, w, __fmaf_rn(a.y, v, __fmul_rn(a.x, u)));
+                y[p] = __fmaf_rn(b.y, w, __fmaf_rn(b.x, v, __fmul_rn(a.w, u)));
+                z[p] = __fmaf_rn(c.x, w, __fmaf_rn(b.w, v, __fmul_rn(b.z, u)));
+            }
+        } else {  // CM3D_OP_A: [u v w 1] . row
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float u = x[p], v = y[p], w = z[p];
+                x[p] = __fmaf_rn(1.0f, a.w, __fmaf_rn(w, a.z, __fmaf_rn(v, a.y, __fmul_rn(u, a.x))));
+                y[p] = __fmaf_rn(1.0f, b.w, __fmaf_rn(w, b.z, __fmaf_rn(v, b.y, __fmul_rn(u, b.x))));
+                z[p] = __fmaf_rn(1.0f, c.w, __fmaf_rn(w, c.z, __fmaf_rn(v, c.y, __fmul_rn(u, c.x))));
+            }
+        }
+    }
+    const float4 k0 = vc.vp[0], k1 = vc.vp[1], k2 = vc.vp[2];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        code[p] = -1;
+        if (!(z[p] > min_depth)) continue;
+        const float r0 = __fmaf_rn(k0.w, 1.0f, __fmaf_rn(k0.z, z[p], __fmaf_rn(k0.y, y[p], __fmul_rn(k0.x, x[p]))));
+        const float r1 = __fmaf_rn(k1.w, 1.0f, __fmaf_rn(k1.z, z[p], __fmaf_rn(k1.y, y[p], __fmul_rn(k1.x, x[p]))));
+        const float r2 = __fmaf_rn(k2.w, 1.0f, __fmaf_rn(k2.z, z[p], __fmaf_rn(k2.y, y[p], __fmul_rn(k2.x, x[p]))));
+        if (r2 > 0.0f && (!(r0 > 0.0f) || !(r1 > 0.0f) || r0 >= __fmul_rn(r2, vc.wcap) || r1 >= __fmul_rn(r2, vc.hcap)))
+            continue;
+        const float u = __fdiv_rn(r0, r2), v = __fdiv_rn(r1, r2);
+        if (u > 0.0f && u < vc.wlim && v > 0.0f && v < vc.hlim)
+            code[p] = (int32_t)floorf(u) | ((int32_t)floorf(v) << 16);
+    }
 }
 
-// Calls f(j) for every instance j (frame-local) the point belongs to; within one vcam the ids
-// come in ascending order.
+// Calls f(j) for every instance j of vcam `vc` whose eroded mask has pixel `code` set; ids ascend.
+template <class F>
+__device__ __forceinline__ void hits_in_vcam(const FrameTables &ft, const VcamS &vc, int32_t code, F f)
+{
+    const int fx = code & 0xffff, fy = code >> 16;
+    const int e = vc.list_begin + vc.list_count;
+    for (int k = vc.list_begin; k < e; ++k) {
+        const int j = ft.list[k];
+        const InstS &s = ft.inst[j];
+        if (fx < s.xmin || fx > s.xmax || fy < s.ymin || fy > s.ymax) continue;
+        const uint32_t wd = __ldg(s.plane + (size_t)fy * s.pitch + (fx >> 5));
+        if ((wd >> (fx & 31)) & 1u) f(j);
+    }
+}
+
+// Single-point form (rare paths): f(j) for every instance the point belongs to.
 template <class F>
 __device__ __forceinline__ void for_each_hit(const FrameTables &ft, float x, float y, float z, int32_t *pix,
                                              int64_t pix_stride, F f)
 {
+    const float xs[1] = {x}, ys[1] = {y}, zs[1] = {z};
     for (int v = 0; v < ft.n_vcams; ++v) {
-        const VcamS &vc = ft.vcam[v];
-        const int32_t code = project_point(vc, ft.min_depth, x, y, z);
-        if (pix) pix[v * pix_stride] = code;
-        if (code < 0) continue;
-        const int fx = code & 0xffff, fy = code >> 16;
-        const int e = vc.list_begin + vc.list_count;
-        for (int k = vc.list_begin; k < e; ++k) {
-            const int j = ft.list[k];
-            const InstS &s = ft.inst[j];
-            if (fx < s.xmin || fx > s.xmax || fy < s.ymin || fy > s.ymax) continue;
-            const uint32_t wd = __ldg(s.plane + (size_t)fy * s.pitch + (fx >> 5));
-            if ((wd >> (fx & 31)) & 1u) f(j);
-        }
+        int32_t code[1];
+        project_n<1>(ft.vcam[v], ft.min_depth, xs, ys, zs, code);
+        if (pix) pix[v * pix_stride] = code[0];
+        if (code[0] >= 0) hits_in_vcam(ft, ft.vcam[v], code[0], f);
     }
 }
 
@@ -252,15 +305,23 @@ k_project_count(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *
         const float4 Z = __ldg(reinterpret_cast<const float4 *>(xyzw + 2 * n_slots + base + s0));
         const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
         uint32_t hw[4] = {0u, 0u, 0u, 0u};
+        const int np = min(4, cnt - s0);
+        for (int v = 0; v < ft.n_vcams; ++v) {
+            const VcamS &vc = ft.vcam[v];
+            int32_t code[4];
+            project_n<4>(vc, ft.min_depth, xs, ys, zs, code);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (s0 + k >= cnt) break;
-            uint32_t h = 0;
-            for_each_hit(ft, xs[k], ys[k], zs[k], pix ? pix + base + s0 + k : nullptr, n_slots, [&](int j) {
-                h = hit_insert(h, (uint32_t)j + 1u);
-                atomicAdd(&s_hist[j], 1);
-            });
-            hw[k] = h;
+            for (int k = 0; k < 4; ++k) {
+                if (k >= np) continue;
+                if (pix) pix[(int64_t)v * n_slots + base + s0 + k] = code[k];
+                if (code[k] < 0) continue;
+                uint32_t h = hw[k];
+                hits_in_vcam(ft, vc, code[k], [&](int j) {
+                    h = hit_insert(h, (uint32_t)j + 1u);
+                    atomicAdd(&s_hist[j], 1);
+                });
+                hw[k] = h;
+            }
         }
         *reinterpret_cast<uint4 *>(hits + base + s0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     }
