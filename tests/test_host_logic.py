@@ -1,0 +1,163 @@
+"""CPU: host-side logic - RLE codec, frame (de)serialisation, batch packing, sharding (gloo, 2 ranks)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_rle_string_codec_round_trip():
+    from cm3d_b200.rle import rle_string_to_runs, runs_to_rle_string
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        runs = rng.integers(0, 5000, rng.integers(1, 60)).astype(np.uint32)
+        s = runs_to_rle_string(runs)
+        assert all(48 <= c < 112 for c in s)
+        assert np.array_equal(rle_string_to_runs(s), runs)
+    # known vector: pycocotools encodes a 4x4 mask with a 2x2 block of ones at rows 1-2, cols 1-2
+    # (column-major) as counts [5,2,2,2,5] -> "52203"
+    assert runs_to_rle_string([5, 2, 2, 2, 5]) == b"52203"
+    assert rle_string_to_runs(b"52203").tolist() == [5, 2, 2, 2, 5]
+
+
+def test_dense_rle_round_trip():
+    from cm3d_b200.synthetic import dense_to_rle, rle_to_dense
+    rng = np.random.default_rng(1)
+    m = (rng.uniform(size=(3, 37, 53)) > 0.6).astype(np.uint8)
+    m[1] = 1
+    m[2] = 0
+    for dense, rle in zip(m, dense_to_rle(m)):
+        assert rle.size == (53, 37)
+        assert np.array_equal(rle_to_dense(rle), dense)
+
+
+def test_frame_arrays_round_trip():
+    from cm3d_b200.frames import frame_from_arrays, frame_to_arrays
+    frame, _ = load_golden("waymo_small")
+    d = frame_to_arrays(frame)
+    f2 = frame_from_arrays(d)
+    d2 = frame_to_arrays(f2)
+    assert sorted(d) == sorted(d2)
+    for k in d:
+        assert np.array_equal(d[k], d2[k], equal_nan=d[k].dtype.kind == "f"), k
+
+
+def test_synthetic_frames_are_deterministic_and_shaped():
+    from cm3d_b200 import synthetic as S
+    a = S.make_frame("c1", 5, scale=0.1)
+    b = S.make_frame("c1", 5, scale=0.1)
+    assert all(np.array_equal(x, y) for x, y in zip(a.sweeps, b.sweeps))
+    assert np.array_equal(a.masks, b.masks)
+    assert a.n_instances == 20 and len(a.cams) == 6 and a.sweeps[0].shape[1] == 5
+    k = S.make_frame("c3", 0, scale=0.05)
+    assert k.dataset == "kitti" and len(k.cams) == 1 and k.masks.shape[1:] == (309, 1024)
+    w = S.make_frame("c4", 0, scale=0.05)
+    assert w.dataset == "waymo" and {m.size for m in w.masks} <= {(1024, 683), (1024, 473)}
+
+
+def test_pack_frames_tables():
+    from cm3d_b200 import batch as B
+    frames = [load_golden(n)[0] for n in ("nusc_small", "kitti_small", "waymo_small")]
+    pb = B.pack_frames(frames)
+    fd = pb.table("frame_desc", B.FR_WORDS)
+    sd = pb.table("sweep_desc", B.SW_WORDS)
+    ts = pb.table("tile_sweep")
+    assert pb.n_frames == 3 and pb.n_sweeps == 5 and pb.masks_kind == "rle"
+    # tiles: contiguous per frame, ceil(npts/1024) per sweep, sweep bases consistent
+    assert fd[0, 0] == 0 and np.array_equal(fd[1:, 0], fd[:-1, 1]) and fd[-1, 1] == pb.n_tiles
+    t = 0
+    for s in range(pb.n_sweeps):
+        nt = -(-int(sd[s, 2]) // B.TILE)
+        assert sd[s, 5] == t and (ts[t:t + nt] == s).all()
+        o = int(np.uint32(sd[s, 0])) | (int(sd[s, 1]) << 32)
+        assert o % 4 == 0                                   # 16-byte aligned sweep starts (bulk copy)
+        t += nt
+    # raw points are copied verbatim
+    o = int(np.uint32(sd[3, 0]))
+    assert np.array_equal(pb.raw[o:o + frames[1].sweeps[0].size], frames[1].sweeps[0].reshape(-1))
+    # instances: frame-major, vcam lists partition the frame's instances
+    assert pb.n_inst == sum(f.n_instances for f in frames)
+    vd = pb.table("vcam_desc", B.VC_WORDS)
+    lst = pb.table("cam_inst_list")
+    for f in range(3):
+        v0, nv, i0, ni = fd[f, 2], fd[f, 3], fd[f, 4], fd[f, 5]
+        got = []
+        for v in range(v0, v0 + nv):
+            got += lst[i0 + vd[v, 15]: i0 + vd[v, 15] + vd[v, 16]].tolist()
+        assert sorted(got) == list(range(ni))
+    assert fd[1, 10] == 4 and fd[0, 10] == 1               # KITTI skips M <= 3 (kitti:1479-1480)
+    assert fd[0, 7] == 1 and fd[1, 7] == 0                 # close-point filter is nuScenes only
+    assert pb.cnt_total == sum((fd[f, 1] - fd[f, 0]) * fd[f, 5] for f in range(3))
+
+
+def test_pack_limits():
+    from cm3d_b200 import batch as B
+    from cm3d_b200 import synthetic as S
+    f = S.make_nuscenes_frame(1, n_sweeps=1, pts_per_sweep=500, n_inst=2, mask_div=8)
+    f.cam_nums = np.zeros(300, np.int32)
+    f.masks = np.zeros((300,) + f.masks.shape[1:], np.uint8)
+    with pytest.raises(ValueError, match="CM3D_ELIMIT"):
+        B.pack_frames([f])
+
+
+def test_shard_indices_and_merge():
+    from cm3d_b200 import shard as SH
+    for n in (0, 1, 7, 64, 28130):
+        for world in (1, 2, 4, 8):
+            for mode in ("interleaved", "blocked"):
+                parts = [SH.shard_indices(n, r, world, mode) for r in range(world)]
+                assert sorted(sum(parts, [])) == list(range(n))
+                assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    merged = SH.merge_shards([{0: "a", 2: "c"}, {1: "b"}], 3)
+    assert merged == ["a", "b", "c"]
+    with pytest.raises(ValueError):
+        SH.merge_shards([{0: "a"}, {0: "b"}], 1)
+    with pytest.raises(ValueError):
+        SH.merge_shards([{0: "a"}], 2)
+
+
+_WORKER = r'''
+import os, sys, pickle
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+from cm3d_b200 import shard as SH, synthetic as S
+from oracle import c_oracle as CO
+
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+N = 6
+load = lambda i: S.make_nuscenes_frame(100 + i, n_sweeps=1, pts_per_sweep=1500, n_inst=4, mask_div=4)
+def lift(frames):      # the oracle stands in for the GPU lifter on this CPU-only box
+    return [CO.lift_frame_c(f, record_pix=False)["medoid_point_idx"].tolist() for f in frames]
+local = SH.lift_sharded(N, load, lift, batch=2, rank=dist.get_rank(), world=2)
+merged = SH.gather_labels(local, N)
+if dist.get_rank() == 0:
+    single = SH.lift_sharded(N, load, lift, batch=4, rank=0, world=1)
+    assert merged == [single[i] for i in range(N)], (merged, single)
+    open(sys.argv[2], "w").write("ok %d" % len(merged))
+else:
+    assert merged is None
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_lift_two_ranks_gloo(tmp_path):
+    """world_size 2 over gloo: each rank lifts its share, rank 0 gathers and the merged labels
+    equal the single-process result."""
+    import socket
+    import subprocess
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    out = tmp_path / "out.txt"
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(out)]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=240) == 0
+    assert out.read_text() == "ok 6"

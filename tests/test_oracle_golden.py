@@ -1,0 +1,80 @@
+"""CPU: the oracles against the golden fixtures (made by oracle/make_golden.py with the reference's
+own utils/pcd.py and kitti_utils.Calibration, imported from /root/reference at generation time)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_c_oracle_matches_golden(name):
+    from oracle import c_oracle as CO
+    frame, d = load_golden(name)
+    r = CO.lift_frame_c(frame)
+    assert r["n_points"] == int(d["n_points"])
+    assert np.array_equal(r["aggr"].view(np.uint32), d["aggr"].view(np.uint32))
+    idx = np.concatenate(r["idx"]) if r["idx"] else np.zeros(0, np.int64)
+    assert np.array_equal(idx, d["seg_point_idx"])
+    assert np.array_equal(np.cumsum([0] + [len(x) for x in r["idx"]]), d["seg_offsets"])
+    assert np.array_equal(r["medoid_local"], d["medoid_local"])
+    assert np.array_equal(r["medoid_point_idx"], d["medoid_point_idx"])
+    has = d["medoid_local"] >= 0
+    assert np.array_equal(r["centroids"][has].view(np.uint32), d["centroids"][has].view(np.uint32))
+    for c in d["pix_cams"]:
+        sel, fx, fy = r["pix"][int(c)]
+        assert np.array_equal(sel, d[f"pix_{c}_idx"])
+        assert np.array_equal(fx, d[f"pix_{c}_fx"])
+        assert np.array_equal(fy, d[f"pix_{c}_fy"])
+
+
+@pytest.mark.parametrize("name", ["nusc_small", "nusc_edge", "kitti_small", "waymo_small"])
+def test_torch_restatement_matches_golden(name):
+    """oracle/ref_lift.py with its own restated helpers (no reference import) reproduces the
+    fixtures that were generated with the reference's helpers injected."""
+    import torch
+    from oracle import ref_lift as RL
+    torch.set_num_threads(1)
+    frame, d = load_golden(name)
+    r = RL.lift_frame(frame)
+    assert np.array_equal(np.ascontiguousarray(r["aggr"]).view(np.uint32), d["aggr"].view(np.uint32))
+    idx = np.concatenate(r["idx"]) if r["idx"] else np.zeros(0, np.int64)
+    assert np.array_equal(idx, d["seg_point_idx"])
+    assert np.array_equal(r["medoid_local"], d["medoid_local"])
+
+
+def test_edge_fixture_covers_the_quirks():
+    """nusc_edge holds: an empty mask, a full-image mask (fx==0 / fy==0 points dropped), a 1-px
+    line (erodes to nothing), a 3x3 block (erodes to one pixel), masks touching the border."""
+    frame, d = load_golden("nusc_edge")
+    cnt = np.diff(d["seg_offsets"])
+    assert cnt[0] == 0 and cnt[2] == 0            # empty mask, eroded-away line
+    assert cnt[1] > 0                             # full image
+    full = d["seg_point_idx"][d["seg_offsets"][1]:d["seg_offsets"][2]]
+    c = int(frame.cam_nums[1])
+    sel = d[f"pix_{c}_idx"]
+    fx, fy = d[f"pix_{c}_fx"], d[f"pix_{c}_fy"]
+    inside = sel[(fx != 0) & (fy != 0) & (fx < 511) & (fy < 287)]
+    # every in-image point of that camera is a member unless its floor is 0 or on the eroded border
+    assert set(full.tolist()) <= set(sel.tolist())
+    assert not (set(sel[(fx == 0) | (fy == 0)].tolist()) & set(full.tolist()))
+    assert (d["medoid_local"][cnt == 0] == -1).all()
+
+
+def test_medoid_oracle_vs_torch_many_sizes():
+    """C medoid (ATen cascade order, IEEE sqrt) against torch.cdist(...).sum(0).argmin() for every
+    M in 1..100 and a few larger sizes, in nuScenes-like global coordinates where cdist's matmul
+    formula is noisy.  Sums may differ by the last bit (torch's vectorised sqrt), the argmin not."""
+    import torch
+    from oracle import c_oracle as CO
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for m in list(range(1, 101)) + [127, 128, 129, 255, 256, 257, 511, 513, 1000, 2049]:
+        p = (rng.normal(0, 2.0, (3, m)) + np.array([[1234.5], [987.25], [1.5]])).astype(np.float32)
+        t = torch.from_numpy(p)
+        ref = torch.cdist(t.T, t.T, p=2).sum(axis=0)
+        j, sums = CO.medoid(p, want_sums=True)
+        rs = ref.numpy()
+        worst = max(worst, float(np.max(np.abs(sums - rs) / np.maximum(np.abs(rs), 1e-6))))
+        assert j == int(torch.argmin(ref)), m
+    assert worst < 1e-6
