@@ -27,6 +27,7 @@ PROTOTYPES = {
     "cm3d_scan_segments": [_P, _P, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P],
     "cm3d_compact_segments": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P],
     "cm3d_medoid": [_P, _L, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "cm3d_pca_obb": [_P, _L, _P, _I, _I, _P, _P, _P],
     "cm3d_selftest_sqrt": [_P, _P],
 }
 EXPORTS = ["cm3d_abi_version", "cm3d_error_string"] + list(PROTOTYPES)

@@ -72,7 +72,7 @@ class PackedBatch:
     frame_inst: np.ndarray = None   # (F+1,) instance ranges
     frame_vcam_cams: List[List[tuple]] = field(default_factory=list)  # per frame [(cam, W, H)]
     tensors: dict = field(default_factory=dict)             # pinned torch views of raw/meta/mask/mask_off
-    algo_bytes: dict = field(default_factory=dict)          # algorithmic bytes per kernel
+    any_kitti: bool = False         # a KITTI frame is in the batch -> Lifter also computes the OBB yaw
 
     def table(self, name: str, words: int = 1) -> np.ndarray:
         o, n = self.off[name], self.off[name + "_n"]
@@ -229,4 +229,5 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
                      bits_words, max_words, sum(f.n_raw_points for f in frames), masks_kind, max_runs,
                      raw, meta, mask, mo[:mask_off_arr.size], off, frame_inst, frame_vcam_cams,
                      {"raw": raw_t, "meta": meta_t, "mask": mask_t, "mask_off": mo_t})
+    pb.any_kitti = any(f.dataset == "kitti" for f in frames)
     return pb

@@ -160,6 +160,7 @@ class LiftResult:
     aggr_points: Optional[np.ndarray] = None   # (rows,N) fp32, only when requested
     pix: Optional[np.ndarray] = None           # (C,N) int32 packed fx|fy<<16 or -1, debug only
     yaw: Optional[np.ndarray] = None           # (I,) fp32 KITTI OBB yaw, nan if n/a
+    obb: Optional[np.ndarray] = None           # (I,16) yaw, centre xyz, wlh, R' row-major (KITTI)
 
     @property
     def counts(self) -> np.ndarray:

@@ -53,6 +53,7 @@ class DeviceOutputs:
     hits: Optional[torch.Tensor] = None
     bits: Optional[torch.Tensor] = None
     bbox: Optional[torch.Tensor] = None
+    obb: Optional[torch.Tensor] = None     # (I,16): yaw, centre, wlh, R' (KITTI frames / want_obb)
 
 
 class Lifter:
@@ -104,7 +105,7 @@ class Lifter:
         return lay
 
     def run(self, db: DeviceBatch, seg_cap: Optional[int] = None, want_pix: bool = False,
-            want_col_sums: bool = False, do_medoid: bool = True) -> DeviceOutputs:
+            want_col_sums: bool = False, do_medoid: bool = True, want_obb: Optional[bool] = None) -> DeviceOutputs:
         pb, dev = db.pb, self.device
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         F, I, T = pb.n_frames, pb.n_inst, pb.n_tiles
@@ -183,8 +184,17 @@ class Lifter:
                    _ptr(o("item_off")), I, max_items, _ptr(medoid_best), _ptr(col_sums), _ptr(o("medoid_local")),
                    _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
             self.launches += 2
+        # ---- KITTI: principal-axes box + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479)
+        obb = None
+        if want_obb is None:
+            want_obb = pb.any_kitti
+        if want_obb and I:
+            obb = torch.empty(I * 16, dtype=torch.float32, device=dev)
+            self._call("pca_obb", "cm3d_pca_obb", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, 4, _ptr(obb),
+                       _ptr(o("errflags")), st)
+            self.launches += 1
         return DeviceOutputs(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, xyzw, tile_cnt, tile_prefix,
-                             pix, col_sums, hits, bits, bbox)
+                             pix, col_sums, hits, bits, bbox, obb)
 
     # ------------------------------------------------------------------ device -> host
     def fetch_labels(self, do: DeviceOutputs, pinned: Optional[torch.Tensor] = None) -> dict:
@@ -203,6 +213,58 @@ class Lifter:
         res["centroid"] = res["centroid"].view(np.float32).reshape(-1, 4)
         return res
 
+    @staticmethod
+    def _split_labels(h: np.ndarray, layout: dict) -> dict:
+        res = {k: h[v[0]:v[0] + v[1]] for k, v in layout.items() if not k.startswith("_")}
+        res["centroid"] = res["centroid"].view(np.float32).reshape(-1, 4)
+        return res
+
+    def lift_packed_stream(self, batches, seg_cap: Optional[int] = None, depth: int = 2):
+        """Pipelined bulk path (config C5: tens of thousands of frames): yields the label dict of
+        every PackedBatch in order.  Batch k+1 is copied host->device on a copy stream while batch
+        k runs on the compute stream; the small result block comes back asynchronously into
+        pinned memory.  A batch whose segment buffers overflow is rerun with the exact size."""
+        dev = self.device
+        copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        inflight = []                       # (pb, db, do, pinned, done_event)
+        pool = []                           # pinned result buffers, reused (cudaHostAlloc is slow)
+
+        def finish(item):
+            pb, db, do, pinned, done = item
+            done.synchronize()
+            lab = self._split_labels(pinned[:do.out.numel()].numpy().copy(), do.layout)
+            pool.append(pinned)
+            need = self.check_flags(lab)
+            if need:                        # rare: rerun this batch synchronously with exact capacity
+                with torch.cuda.stream(comp_s):
+                    do2 = self.run(db, seg_cap=need)
+                    lab = self.fetch_labels(do2)
+                if self.check_flags(lab):
+                    raise N.Cm3dError("segment capacity retry failed")
+            return lab
+
+        for pb in batches:
+            with torch.cuda.stream(copy_s):
+                db = self.upload(pb)
+                up = torch.cuda.Event()
+                up.record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(up)
+                do = self.run(db, seg_cap=seg_cap)
+                pinned = next((b for b in pool if b.numel() >= do.out.numel()), None)
+                if pinned is None:
+                    pinned = torch.empty(do.out.numel(), dtype=torch.int32, pin_memory=True)
+                else:
+                    pool.remove(pinned)
+                pinned[:do.out.numel()].copy_(do.out, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(comp_s)
+            inflight.append((pb, db, do, pinned, done))
+            if len(inflight) >= depth:
+                yield finish(inflight.pop(0))
+        while inflight:
+            yield finish(inflight.pop(0))
+
     def check_flags(self, labels: dict):
         e = labels["errflags"]
         if e[1]:
@@ -220,6 +282,7 @@ class Lifter:
             tile_cnt = do.tile_cnt.cpu().numpy()
         pix_all = do.pix.view(16, -1).cpu().numpy() if (with_pix and do.pix is not None) else None
         fdesc = pb.table("frame_desc", 12)
+        obb_all = do.obb.view(-1, 16).cpu().numpy() if do.obb is not None else None
         out = []
         for f in range(pb.n_frames):
             i0, i1 = int(pb.frame_inst[f]), int(pb.frame_inst[f + 1])
@@ -231,6 +294,9 @@ class Lifter:
                 medoid_local=labels["medoid_local"][i0:i1].copy(),
                 medoid_point_idx=labels["medoid_point_idx"][i0:i1].copy(),
                 centroids=labels["centroid"][i0:i1, :3].copy())
+            if obb_all is not None:
+                r.yaw = obb_all[i0:i1, 0].copy()
+                r.obb = obb_all[i0:i1].copy()
             if with_points:
                 tb, te = int(fdesc[f, 0]), int(fdesc[f, 1])
                 keep = (np.arange(TILE)[None, :] < tile_cnt[tb:te, None]).reshape(-1)

@@ -16,6 +16,7 @@
  *   cm3d_scan_segments      (no reference counterpart: sizes of the boolean-index results)
  *   cm3d_compact_segments   src/nuscenes/2d_to_3d.py:617-620 (track_points, gather)
  *   cm3d_medoid             src/nuscenes/2d_to_3d.py:116-119,641-663 (cdist medoid, centroid)
+ *   cm3d_pca_obb            src/kitti/2d_to_3d.py:855-876,1524 (open3d OBB -> yaw; parity unpinned)
  *
  * Conventions: every pointer is a DEVICE pointer; the caller (PyTorch) owns and
  * sizes every buffer; nothing is allocated, nothing throws; all launches are
@@ -165,6 +166,15 @@ int cm3d_medoid(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off,
                 int max_items, unsigned long long *medoid_best, float *col_sums,
                 int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
                 const int32_t *errflags, void *stream);
+
+/* ---- KITTI orientation (PARITY UNPINNED: open3d is not in the reference tree) ------------------ */
+
+/* Principal-axes box of every instance with at least min_pts points and the reference's yaw
+ * (src/kitti/2d_to_3d.py:855-876,1524): obb[16*i..] = yaw, centre xyz, wlh (after the reference's
+ * axis shuffle), R' row-major (9 floats); NaN for skipped instances.  PCA of the member points,
+ * conventions in csrc/obb.cu. */
+int cm3d_pca_obb(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
+                 int min_pts, float *obb, const int32_t *errflags, void *stream);
 
 /* Self-test: counts (adds to *mismatches) the floats in [2^-101, FLT_MAX] U {0} on which the
  * medoid kernel's branch-free square root differs from IEEE sqrt.rn.f32.  Must stay 0. */

@@ -78,3 +78,26 @@ def test_medoid_oracle_vs_torch_many_sizes():
         worst = max(worst, float(np.max(np.abs(sums - rs) / np.maximum(np.abs(rs), 1e-6))))
         assert j == int(torch.argmin(ref)), m
     assert worst < 1e-6
+
+
+def test_obb_oracle_yaw_matches_live_scipy_on_proper_rotations():
+    """oracle/obb_oracle.py restates scipy 1.11.4's from_matrix/as_euler; where the installed scipy
+    accepts the input (right-handed R') both must agree."""
+    from scipy.spatial.transform import Rotation
+    from oracle import obb_oracle as O
+    rng = np.random.default_rng(3)
+    proper = improper = 0
+    for _ in range(200):
+        m = int(rng.integers(4, 300))
+        p = rng.uniform(-0.5, 0.5, (m, 3)) * rng.uniform(0.3, 5, 3)
+        p = (p @ Rotation.from_euler("zyx", rng.uniform(-3, 3, 3)).as_matrix().T + rng.uniform(-20, 20, 3)).astype(np.float32)
+        center, wlh, R = O.get_depth_bbox(p)
+        assert abs(abs(np.linalg.det(R)) - 1) < 1e-9
+        if np.linalg.det(R) > 0:
+            ref = Rotation.from_matrix(R).as_euler("zyx")[0]
+            assert abs(((O.yaw_of(R) - ref + np.pi) % (2 * np.pi)) - np.pi) < 1e-9
+            proper += 1
+        else:
+            assert np.isfinite(O.yaw_of(R))
+            improper += 1
+    assert proper > 20 and improper > 20
