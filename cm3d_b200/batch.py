@@ -25,6 +25,7 @@ TILE = 1024
 MAX_INST = 254
 MAX_VCAMS = 16
 MEDOID_COLS = 256
+CELL = 32
 SW_WORDS, FR_WORDS, VC_WORDS, IN_WORDS, ERR_WORDS = 8, 12, 20, 8, 4
 
 
@@ -72,6 +73,8 @@ class PackedBatch:
     frame_inst: np.ndarray = None   # (F+1,) instance ranges
     frame_vcam_cams: List[List[tuple]] = field(default_factory=list)  # per frame [(cam, W, H)]
     tensors: dict = field(default_factory=dict)             # pinned torch views of raw/meta/mask/mask_off
+    grid_words: int = 0             # words of the per-vcam instance lookup grids
+    max_cells: int = 0
     any_kitti: bool = False         # a KITTI frame is in the batch -> Lifter also computes the OBB yaw
 
     def table(self, name: str, words: int = 1) -> np.ndarray:
@@ -120,7 +123,7 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
     frame_inst = np.zeros(F + 1, np.int64)
 
     si = ti = ii = 0
-    cnt_total = bits_words = max_words = 0
+    cnt_total = bits_words = max_words = grid_words = max_cells = 0
     max_inst_pf = 0
     mask_chunks, mask_off = [], [0]
     max_runs = 0
@@ -161,6 +164,10 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
             chains.append(encode_chain(cam.ops))
             row[1:13] = cam.viewpad34().reshape(-1).view(np.int32)
             row[13], row[14], row[15], row[16] = k[1], k[2], lb, len(mem)
+            gnx, gny = -(-k[1] // CELL), -(-k[2] // CELL)
+            row[17], row[18], row[19] = fi, grid_words, gnx
+            grid_words += gnx * gny * ((len(mem) + 31) // 32)
+            max_cells = max(max_cells, gnx * gny)
             cam_inst_list[ii + lb: ii + lb + len(mem)] = mem
             lb += len(mem)
             vcam_rows.append(row)
@@ -230,4 +237,5 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
                      raw, meta, mask, mo[:mask_off_arr.size], off, frame_inst, frame_vcam_cams,
                      {"raw": raw_t, "meta": meta_t, "mask": mask_t, "mask_off": mo_t})
     pb.any_kitti = any(f.dataset == "kitti" for f in frames)
+    pb.grid_words, pb.max_cells = grid_words, max_cells
     return pb

@@ -111,6 +111,8 @@ struct VcamS {
     float wlim, hlim;              // float(W-1), float(H-1): the reference's strict upper bounds
     float wcap, hcap;              // float(W), float(H): conservative reject bounds (see project_n)
     int list_begin, list_count;
+    const uint32_t *grid;          // instance lookup grid of this vcam
+    int grid_nx, grid_nwords;
 };
 struct InstS {
     int xmin, ymin, xmax, ymax;   // eroded bbox, clamped to >= 1 (the reference drops fx==0 / fy==0)
@@ -132,7 +134,8 @@ __device__ __forceinline__ void load_frame_tables(FrameTables &ft, const int32_t
                                                   const int32_t *__restrict__ inst_desc,
                                                   const int32_t *__restrict__ inst_bbox,
                                                   const uint32_t *__restrict__ chains,
-                                                  const uint32_t *__restrict__ bits)
+                                                  const uint32_t *__restrict__ bits,
+                                                  const uint32_t *__restrict__ vcam_grid)
 {
     const int nv = fd[CM3D_FR_NVCAMS], ni = fd[CM3D_FR_NINST];
     const int v0 = fd[CM3D_FR_VCAM_BEGIN], i0 = fd[CM3D_FR_INST_BEGIN], l0 = fd[CM3D_FR_LIST_BEGIN];
@@ -156,7 +159,12 @@ __device__ __forceinline__ void load_frame_tables(FrameTables &ft, const int32_t
         else if (wd == 12) { ft.vcam[v].wlim = (float)(vd[CM3D_VC_W] - 1); ft.vcam[v].wcap = (float)vd[CM3D_VC_W]; }
         else if (wd == 13) { ft.vcam[v].hlim = (float)(vd[CM3D_VC_H] - 1); ft.vcam[v].hcap = (float)vd[CM3D_VC_H]; }
         else if (wd == 14) ft.vcam[v].list_begin = vd[CM3D_VC_LIST_BEGIN];
-        else ft.vcam[v].list_count = vd[CM3D_VC_LIST_COUNT];
+        else {
+            ft.vcam[v].list_count = vd[CM3D_VC_LIST_COUNT];
+            ft.vcam[v].grid = vcam_grid + vd[CM3D_VC_GRID_OFF];
+            ft.vcam[v].grid_nx = vd[CM3D_VC_GRID_NX];
+            ft.vcam[v].grid_nwords = (vd[CM3D_VC_LIST_COUNT] + 31) >> 5;
+        }
     }
     for (int j = threadIdx.x; j < ni; j += blockDim.x) {
         const int32_t *d = inst_desc + (size_t)(i0 + j) * CM3D_IN_WORDS;
@@ -230,17 +238,23 @@ __device__ __forceinline__ void project_n(const VcamS &vc, float min_depth, cons
 }
 
 // Calls f(j) for every instance j of vcam `vc` whose eroded mask has pixel `code` set; ids ascend.
+// The cell grid narrows the vcam's instance list to those whose bbox touches the pixel's cell.
 template <class F>
 __device__ __forceinline__ void hits_in_vcam(const FrameTables &ft, const VcamS &vc, int32_t code, F f)
 {
     const int fx = code & 0xffff, fy = code >> 16;
-    const int e = vc.list_begin + vc.list_count;
-    for (int k = vc.list_begin; k < e; ++k) {
-        const int j = ft.list[k];
-        const InstS &s = ft.inst[j];
-        if (fx < s.xmin || fx > s.xmax || fy < s.ymin || fy > s.ymax) continue;
-        const uint32_t wd = __ldg(s.plane + (size_t)fy * s.pitch + (fx >> 5));
-        if ((wd >> (fx & 31)) & 1u) f(j);
+    const uint32_t *cell = vc.grid + (size_t)((fy / CM3D_CELL) * vc.grid_nx + fx / CM3D_CELL) * vc.grid_nwords;
+    for (int w = 0; w < vc.grid_nwords; ++w) {
+        uint32_t cand = __ldg(cell + w);
+        while (cand) {
+            const int k = vc.list_begin + w * 32 + (__ffs(cand) - 1);
+            cand &= cand - 1u;
+            const int j = ft.list[k];
+            const InstS &s = ft.inst[j];
+            if (fx < s.xmin || fx > s.xmax || fy < s.ymin || fy > s.ymax) continue;
+            const uint32_t wd = __ldg(s.plane + (size_t)fy * s.pitch + (fx >> 5));
+            if ((wd >> (fx & 31)) & 1u) f(j);
+        }
     }
 }
 
@@ -255,6 +269,33 @@ __device__ __forceinline__ void for_each_hit(const FrameTables &ft, float x, flo
         project_n<1>(ft.vcam[v], ft.min_depth, xs, ys, zs, code);
         if (pix) pix[v * pix_stride] = code[0];
         if (code[0] >= 0) hits_in_vcam(ft, ft.vcam[v], code[0], f);
+    }
+}
+
+// One thread per grid cell of one vcam: bit k of the cell = "bbox of the vcam's k-th instance
+// (eroded pixels, fx/fy >= 1) touches the cell".
+__global__ void __launch_bounds__(256)
+k_build_vcam_grid(const int32_t *__restrict__ vcam_desc, const int32_t *__restrict__ frame_desc,
+                  const int32_t *__restrict__ cam_inst_list, const int32_t *__restrict__ inst_bbox,
+                  uint32_t *__restrict__ vcam_grid)
+{
+    const int32_t *vd = vcam_desc + (size_t)blockIdx.y * CM3D_VC_WORDS;
+    const int nx = vd[CM3D_VC_GRID_NX], ny = (vd[CM3D_VC_H] + CM3D_CELL - 1) / CM3D_CELL;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nx * ny) return;
+    const int32_t *fd = frame_desc + (size_t)vd[CM3D_VC_FRAME] * CM3D_FR_WORDS;
+    const int32_t *list = cam_inst_list + fd[CM3D_FR_LIST_BEGIN] + vd[CM3D_VC_LIST_BEGIN];
+    const int n = vd[CM3D_VC_LIST_COUNT], nwords = (n + 31) >> 5;
+    const int cy = c / nx, cx = c - cy * nx;
+    const int x0 = cx * CM3D_CELL, x1 = x0 + CM3D_CELL - 1, y0 = cy * CM3D_CELL, y1 = y0 + CM3D_CELL - 1;
+    uint32_t *out = vcam_grid + vd[CM3D_VC_GRID_OFF] + (size_t)c * nwords;
+    for (int w = 0; w < nwords; ++w) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32 && w * 32 + b < n; ++b) {
+            const int32_t *bb = inst_bbox + (size_t)(fd[CM3D_FR_INST_BEGIN] + list[w * 32 + b]) * 4;
+            if (bb[0] <= x1 && bb[2] >= x0 && bb[1] <= y1 && bb[3] >= y0) m |= 1u << b;
+        }
+        out[w] = m;
     }
 }
 
@@ -283,8 +324,8 @@ k_project_count(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *
                 const int32_t *__restrict__ frame_desc, const int32_t *__restrict__ vcam_desc,
                 const int32_t *__restrict__ cam_inst_list, const int32_t *__restrict__ inst_desc,
                 const int32_t *__restrict__ inst_bbox, const uint32_t *__restrict__ chains,
-                const uint32_t *__restrict__ bits, uint32_t *__restrict__ hits,
-                uint16_t *__restrict__ tile_inst_cnt, int32_t *__restrict__ pix)
+                const uint32_t *__restrict__ bits, const uint32_t *__restrict__ vcam_grid,
+                uint32_t *__restrict__ hits, uint16_t *__restrict__ tile_inst_cnt, int32_t *__restrict__ pix)
 {
     __shared__ FrameTables ft;
     __shared__ int s_hist[CM3D_MAX_INST + 2];
@@ -292,7 +333,7 @@ k_project_count(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *
     const int t = blockIdx.x;
     const int f = sweep_desc[(size_t)tile_sweep[t] * CM3D_SW_WORDS + CM3D_SW_FRAME];
     const int32_t *fd = frame_desc + (size_t)f * CM3D_FR_WORDS;
-    load_frame_tables(ft, fd, vcam_desc, cam_inst_list, inst_desc, inst_bbox, chains, bits);
+    load_frame_tables(ft, fd, vcam_desc, cam_inst_list, inst_desc, inst_bbox, chains, bits, vcam_grid);
     for (int j = threadIdx.x; j < CM3D_MAX_INST + 2; j += blockDim.x) s_hist[j] = 0;
     __syncthreads();
 
@@ -455,7 +496,8 @@ k_compact(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *__rest
           const int32_t *__restrict__ vcam_desc, const int32_t *__restrict__ cam_inst_list,
           const int32_t *__restrict__ inst_desc, const int32_t *__restrict__ inst_bbox,
           const uint32_t *__restrict__ chains, const uint32_t *__restrict__ bits,
-          const uint32_t *__restrict__ hits, const int32_t *__restrict__ tile_inst_base,
+          const uint32_t *__restrict__ vcam_grid, const uint32_t *__restrict__ hits,
+          const int32_t *__restrict__ tile_inst_base,
           const int32_t *__restrict__ seg_off, int32_t *__restrict__ seg_point_idx,
           float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *__restrict__ errflags)
 {
@@ -498,7 +540,7 @@ k_compact(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *__rest
         s_base[j] = seg_off[fd[CM3D_FR_INST_BEGIN] + j] +
                     tile_inst_base[(size_t)fd[CM3D_FR_CNT_OFF] + (size_t)j * ntf + tl];
     const bool have_ovf = s_ovf != 0;
-    if (have_ovf) load_frame_tables(ft, fd, vcam_desc, cam_inst_list, inst_desc, inst_bbox, chains, bits);
+    if (have_ovf) load_frame_tables(ft, fd, vcam_desc, cam_inst_list, inst_desc, inst_bbox, chains, bits, vcam_grid);
     __syncthreads();
 
     const float *gx = xyzw, *gy = xyzw + n_slots, *gz = xyzw + 2 * n_slots, *gw = xyzw + 3 * n_slots;
@@ -574,6 +616,19 @@ extern "C" const char *cm3d_error_string(int code)
     return "unknown cm3d error";
 }
 
+extern "C" int cm3d_build_vcam_grid(const int32_t *vcam_desc, int n_vcams, int max_cells, const int32_t *frame_desc,
+                                    const int32_t *cam_inst_list, const int32_t *inst_bbox, uint32_t *vcam_grid,
+                                    void *stream)
+{
+    if (n_vcams < 0 || max_cells < 0) return CM3D_EINVAL;
+    if (n_vcams == 0 || max_cells == 0) return CM3D_OK;
+    if (!vcam_desc || !frame_desc || !cam_inst_list || !inst_bbox || !vcam_grid) return CM3D_EINVAL;
+    dim3 grid((max_cells + 255) / 256, n_vcams);
+    k_build_vcam_grid<<<grid, 256, 0, (cudaStream_t)stream>>>(vcam_desc, frame_desc, cam_inst_list, inst_bbox, vcam_grid);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}
+
 extern "C" int cm3d_aggregate_sweeps(const float *raw, const int32_t *tile_sweep, int n_tiles,
                                      const int32_t *sweep_desc, const int32_t *frame_desc,
                                      const uint32_t *chains, float *xyzw, int32_t *tile_cnt, void *stream)
@@ -592,17 +647,17 @@ extern "C" int cm3d_project_membership(const float *xyzw, const int32_t *tile_cn
                                        int n_tiles, const int32_t *sweep_desc, const int32_t *frame_desc,
                                        const int32_t *vcam_desc, const int32_t *cam_inst_list,
                                        const int32_t *inst_desc, const int32_t *inst_bbox,
-                                       const uint32_t *chains, const uint32_t *bits, uint32_t *hits,
-                                       uint16_t *tile_inst_cnt, int32_t *pix, void *stream)
+                                       const uint32_t *chains, const uint32_t *bits, const uint32_t *vcam_grid,
+                                       uint32_t *hits, uint16_t *tile_inst_cnt, int32_t *pix, void *stream)
 {
     if (n_tiles < 0) return CM3D_EINVAL;
     if (n_tiles == 0) return CM3D_OK;
     if (!xyzw || !tile_cnt || !tile_sweep || !sweep_desc || !frame_desc || !vcam_desc || !cam_inst_list ||
-        !inst_desc || !inst_bbox || !chains || !bits || !hits || !tile_inst_cnt)
+        !inst_desc || !inst_bbox || !chains || !bits || !vcam_grid || !hits || !tile_inst_cnt)
         return CM3D_EINVAL;
     k_project_count<<<n_tiles, kBlock, 0, (cudaStream_t)stream>>>(
         xyzw, (int64_t)n_tiles * kTile, tile_cnt, tile_sweep, sweep_desc, frame_desc, vcam_desc, cam_inst_list,
-        inst_desc, inst_bbox, chains, bits, hits, tile_inst_cnt, pix);
+        inst_desc, inst_bbox, chains, bits, vcam_grid, hits, tile_inst_cnt, pix);
     CM3D_LAUNCH_CHECK();
     return CM3D_OK;
 }
@@ -637,7 +692,8 @@ extern "C" int cm3d_compact_segments(const float *xyzw, const int32_t *tile_cnt,
                                      const int32_t *frame_desc, const int32_t *vcam_desc,
                                      const int32_t *cam_inst_list, const int32_t *inst_desc,
                                      const int32_t *inst_bbox, const uint32_t *chains, const uint32_t *bits,
-                                     const uint32_t *hits, const int32_t *tile_inst_base,
+                                     const uint32_t *vcam_grid, const uint32_t *hits,
+                                     const int32_t *tile_inst_base,
                                      const int32_t *seg_off, int32_t *seg_point_idx, float *seg_xyzw,
                                      int64_t seg_cap, int max_inst_per_frame, const int32_t *errflags,
                                      void *stream)
@@ -646,14 +702,15 @@ extern "C" int cm3d_compact_segments(const float *xyzw, const int32_t *tile_cnt,
     if (max_inst_per_frame > CM3D_MAX_INST) return CM3D_ELIMIT;
     if (n_tiles == 0) return CM3D_OK;
     if (!xyzw || !tile_cnt || !tile_prefix || !tile_sweep || !sweep_desc || !frame_desc || !vcam_desc ||
-        !cam_inst_list || !inst_desc || !inst_bbox || !chains || !bits || !hits || !tile_inst_base || !seg_off ||
+        !cam_inst_list || !inst_desc || !inst_bbox || !chains || !bits || !vcam_grid || !hits || !tile_inst_base ||
+        !seg_off ||
         !seg_point_idx || !seg_xyzw || !errflags)
         return CM3D_EINVAL;
     const size_t smem = ((kGroups * max_inst_per_frame * 2 + 15) & ~15) + max_inst_per_frame * sizeof(int) + 16;
     k_compact<<<n_tiles, kBlock, smem, (cudaStream_t)stream>>>(
         xyzw, (int64_t)n_tiles * kTile, tile_cnt, tile_prefix, tile_sweep, sweep_desc, frame_desc, vcam_desc,
-        cam_inst_list, inst_desc, inst_bbox, chains, bits, hits, tile_inst_base, seg_off, seg_point_idx, seg_xyzw,
-        seg_cap, errflags);
+        cam_inst_list, inst_desc, inst_bbox, chains, bits, vcam_grid, hits, tile_inst_base, seg_off, seg_point_idx,
+        seg_xyzw, seg_cap, errflags);
     CM3D_LAUNCH_CHECK();
     return CM3D_OK;
 }

@@ -141,6 +141,12 @@ class Lifter:
                    _ptr(bbox), st)
             self.launches += 2
 
+        vcam_grid = torch.empty(max(pb.grid_words, 1), **i32)
+        if I:
+            self._call("vcam_grid", "cm3d_build_vcam_grid", _ptr(db.tab("vcam_desc")), pb.n_vcams, pb.max_cells,
+                       _ptr(db.tab("frame_desc")), _ptr(db.tab("cam_inst_list")), _ptr(bbox), _ptr(vcam_grid), st)
+            self.launches += 1
+
         # ---- sweeps -> aggregated cloud
         xyzw = torch.empty(4 * n_slots, dtype=torch.float32, device=dev)
         tile_cnt = torch.empty(max(T, 1), **i32)
@@ -157,7 +163,7 @@ class Lifter:
         self._call("project_count", "cm3d_project_membership", _ptr(xyzw), _ptr(tile_cnt), _ptr(db.tab("tile_sweep")), T,
                _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
                _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
-               _ptr(hits), _ptr(tile_inst_cnt), _ptr(pix), st)
+               _ptr(vcam_grid), _ptr(hits), _ptr(tile_inst_cnt), _ptr(pix), st)
         self.launches += 1 if T else 0
 
         # ---- scans, ordered compaction + gather
@@ -172,7 +178,7 @@ class Lifter:
         self._call("compact", "cm3d_compact_segments", _ptr(xyzw), _ptr(tile_cnt), _ptr(tile_prefix), _ptr(db.tab("tile_sweep")),
                T, _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
                _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
-               _ptr(hits), _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(seg_point_idx), _ptr(seg_xyzw),
+               _ptr(vcam_grid), _ptr(hits), _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(seg_point_idx), _ptr(seg_xyzw),
                seg_cap, pb.max_inst_per_frame, _ptr(o("errflags")), st)
         self.launches += 1 if T else 0
 

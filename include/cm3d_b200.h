@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 2
+#define CM3D_ABI_VERSION 3
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
@@ -77,7 +77,9 @@ enum { CM3D_FR_TILE_BEGIN = 0, CM3D_FR_TILE_END, CM3D_FR_VCAM_BEGIN, CM3D_FR_NVC
 /* vcam_desc[v][CM3D_VC_WORDS]: one per (camera, mask size) of a frame */
 enum { CM3D_VC_CHAIN = 0, CM3D_VC_VIEWPAD = 1 /* 12 floats */, CM3D_VC_W = 13, CM3D_VC_H,
        CM3D_VC_LIST_BEGIN /* into cam_inst_list, relative to the frame's LIST_BEGIN */,
-       CM3D_VC_LIST_COUNT, CM3D_VC_WORDS = 20 };
+       CM3D_VC_LIST_COUNT, CM3D_VC_FRAME, CM3D_VC_GRID_OFF /* word offset into vcam_grid */,
+       CM3D_VC_GRID_NX /* cells per row, ceil(W/CM3D_CELL) */, CM3D_VC_WORDS = 20 };
+#define CM3D_CELL 32            /* pixels per side of a vcam_grid cell */
 /* inst_desc[i][CM3D_IN_WORDS] */
 enum { CM3D_IN_BITS_LO = 0, CM3D_IN_BITS_HI, CM3D_IN_W, CM3D_IN_H, CM3D_IN_PITCH, CM3D_IN_VCAM,
        CM3D_IN_FRAME, CM3D_IN_LOCAL, CM3D_IN_WORDS };
@@ -107,6 +109,13 @@ int cm3d_masks_fill_rle(const uint32_t *runs, const int64_t *run_off, uint32_t *
 int cm3d_masks_erode3x3(const uint32_t *bits_in, const int32_t *inst_desc, int n_inst, int max_words,
                         uint32_t *bits_out, int32_t *bbox, void *stream);
 
+/* Instance lookup grid: for every vcam, cell (cx,cy) of CM3D_CELL^2 pixels holds
+ * ceil(list_count/32) words whose bit k says "the eroded bbox of the vcam's k-th instance touches
+ * this cell" (vcam_grid[GRID_OFF + (cy*NX + cx)*nwords + k/32]).  max_cells = largest NX*NY. */
+int cm3d_build_vcam_grid(const int32_t *vcam_desc, int n_vcams, int max_cells, const int32_t *frame_desc,
+                         const int32_t *cam_inst_list, const int32_t *inst_bbox, uint32_t *vcam_grid,
+                         void *stream);
+
 /* ---- sweeps -> aggregated cloud (tile-compacted SoA) ---------------------------------------- */
 
 /* xyzw: 4 arrays of n_slots floats (x | y | z | 4th row), n_slots = n_tiles*CM3D_TILE.
@@ -126,8 +135,8 @@ int cm3d_project_membership(const float *xyzw, const int32_t *tile_cnt, const in
                             int n_tiles, const int32_t *sweep_desc, const int32_t *frame_desc,
                             const int32_t *vcam_desc, const int32_t *cam_inst_list,
                             const int32_t *inst_desc, const int32_t *inst_bbox,
-                            const uint32_t *chains, const uint32_t *bits, uint32_t *hits,
-                            uint16_t *tile_inst_cnt, int32_t *pix, void *stream);
+                            const uint32_t *chains, const uint32_t *bits, const uint32_t *vcam_grid,
+                            uint32_t *hits, uint16_t *tile_inst_cnt, int32_t *pix, void *stream);
 
 /* Scans.  tile_prefix[t] = index in the frame's aggr_pc_points of tile t's first point;
  * frame_n[f] = N of frame f; tile_inst_base = exclusive prefix of tile_inst_cnt over the
@@ -149,7 +158,7 @@ int cm3d_compact_segments(const float *xyzw, const int32_t *tile_cnt, const int3
                           const int32_t *frame_desc, const int32_t *vcam_desc,
                           const int32_t *cam_inst_list, const int32_t *inst_desc,
                           const int32_t *inst_bbox, const uint32_t *chains, const uint32_t *bits,
-                          const uint32_t *hits, const int32_t *tile_inst_base,
+                          const uint32_t *vcam_grid, const uint32_t *hits, const int32_t *tile_inst_base,
                           const int32_t *seg_off, int32_t *seg_point_idx, float *seg_xyzw,
                           int64_t seg_cap, int max_inst_per_frame, const int32_t *errflags,
                           void *stream);
