@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libcm3d_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -25,9 +25,10 @@ PROTOTYPES = {
     "cm3d_aggregate_sweeps": [_P, _P, _I, _P, _P, _P, _P, _P, _P],
     "cm3d_build_vcam_grid": [_P, _I, _I, _P, _P, _P, _P, _P],
     "cm3d_project_membership": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "cm3d_scan_segments": [_P, _P, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P],
+    "cm3d_scan_segments": [_P, _P, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "cm3d_compact_segments": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P],
-    "cm3d_medoid": [_P, _L, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "cm3d_medoid": [_P, _L, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "cm3d_medoid_items": [_I, _I],
     "cm3d_pca_obb": [_P, _L, _P, _I, _I, _P, _P, _P],
     "cm3d_selftest_sqrt": [_P, _P],
 }

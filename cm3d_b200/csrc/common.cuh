@@ -58,6 +58,22 @@ __device__ __forceinline__ void apply_chain(const uint32_t *__restrict__ chain, 
     }
 }
 
+// ------------------------------------------------------------------ medoid work items
+constexpr int kCols = CM3D_MEDOID_COLS;   // columns of the distance matrix per full medoid item
+constexpr int kSmallM = 32;               // instances below this size are one generic item
+
+// Work items of an instance with m members (0 when it has fewer than min_pts):
+//   m <  kSmallM : one generic item (every column, normal and tail, in one block);
+//   m >= kSmallM : ceil(full/kCols) items over the `full` = (m/32)*32 single-accumulator columns,
+//                  plus one tail item for the last m%32 columns (four threads per column).
+__host__ __device__ inline int medoid_items(int m, int min_pts)
+{
+    if (m < (min_pts > 1 ? min_pts : 1)) return 0;
+    if (m < kSmallM) return 1;
+    const int full = (m / 32) * 32;
+    return (full + kCols - 1) / kCols + ((m & 31) ? 1 : 0);
+}
+
 __device__ __forceinline__ int64_t join64(int32_t lo, int32_t hi)
 {
     return (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);

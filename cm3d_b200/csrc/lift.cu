@@ -410,59 +410,89 @@ k_scan_rows(const int32_t *__restrict__ tile_cnt, const uint16_t *__restrict__ t
     }
 }
 
-// k_scan_batch: one block; seg_off / item_off over all instances of the batch.
+// k_scan_batch: one block.  seg_off = exclusive prefix of the member counts over all instances of
+// the batch; then the medoid schedule: instances are ordered by their number of work items,
+// largest first (64 buckets; the medoid grid is dynamic, so the long items start early and the
+// launch has a short tail), item_inst[p] = the p-th instance of that order and item_off = the
+// exclusive prefix of the item counts in that order.
 __global__ void __launch_bounds__(1024)
 k_scan_batch(const int32_t *__restrict__ seg_count, const int32_t *__restrict__ inst_desc,
              const int32_t *__restrict__ frame_desc, int n_inst_total, int64_t seg_cap,
-             int32_t *__restrict__ seg_off, int32_t *__restrict__ item_off,
+             int32_t *__restrict__ seg_off, int32_t *__restrict__ item_off, int32_t *__restrict__ item_inst,
              unsigned long long *__restrict__ medoid_best, int32_t *__restrict__ errflags)
 {
     __shared__ long long s_wa[32];
-    __shared__ int s_wb[32];
     __shared__ long long s_ca;
-    __shared__ int s_cb;
+    __shared__ int s_hist[64], s_cursor[64];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { s_ca = 0; s_cb = 0; }
+    if (threadIdx.x == 0) s_ca = 0;
+    if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
     __syncthreads();
+    // ---- seg_off (seg_count is staged in seg_off[1..]: element i+1 is read before it is written)
     for (int base = 0; base < n_inst_total; base += blockDim.x) {
         const int i = base + threadIdx.x;
-        long long a = 0;
-        int b = 0;
-        if (i < n_inst_total) {
-            const int m = seg_count[i];
-            const int f = inst_desc[(size_t)i * CM3D_IN_WORDS + CM3D_IN_FRAME];
-            const int minp = max(frame_desc[(size_t)f * CM3D_FR_WORDS + CM3D_FR_MIN_MEDOID_PTS], 1);
-            a = m;
-            b = m >= minp ? (m + CM3D_MEDOID_COLS - 1) / CM3D_MEDOID_COLS : 0;
-            medoid_best[i] = ~0ull;
-        }
+        const long long a = i < n_inst_total ? seg_count[i] : 0;
+        if (i < n_inst_total) medoid_best[i] = ~0ull;
         long long ia = a;
-        int ib = b;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const long long ua = __shfl_up_sync(0xffffffffu, ia, o);
-            const int ub = __shfl_up_sync(0xffffffffu, ib, o);
-            if (lane >= (unsigned)o) { ia += ua; ib += ub; }
+            if (lane >= (unsigned)o) ia += ua;
         }
-        if (lane == 31) { s_wa[warp] = ia; s_wb[warp] = ib; }
+        if (lane == 31) s_wa[warp] = ia;
         __syncthreads();
         long long oa = s_ca;
-        int ob = s_cb;
-        for (unsigned w = 0; w < warp; ++w) { oa += s_wa[w]; ob += s_wb[w]; }
-        if (i < n_inst_total) {
-            const long long ex = oa + ia - a;
-            seg_off[i] = (int32_t)min(ex, (long long)0x7fffffff);
-            item_off[i] = ob + ib - b;
-        }
+        for (unsigned w = 0; w < warp; ++w) oa += s_wa[w];
+        if (i < n_inst_total) seg_off[i] = (int32_t)min(oa + ia - a, (long long)0x7fffffff);
         __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) { s_ca = oa + ia; s_cb = ob + ib; }
+        if (threadIdx.x == blockDim.x - 1) s_ca = oa + ia;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         seg_off[n_inst_total] = (int32_t)min(s_ca, (long long)0x7fffffff);
-        item_off[n_inst_total] = s_cb;
         if (s_ca > seg_cap) errflags[CM3D_ERR_SEG_OVERFLOW] = (int32_t)min(s_ca, (long long)0x7fffffff);
     }
+    __syncthreads();
+    // ---- medoid schedule
+    auto items_of = [&](int i) {
+        const int m = seg_off[i + 1] - seg_off[i];
+        const int f = inst_desc[(size_t)i * CM3D_IN_WORDS + CM3D_IN_FRAME];
+        return medoid_items(m, frame_desc[(size_t)f * CM3D_FR_WORDS + CM3D_FR_MIN_MEDOID_PTS]);
+    };
+    for (int i = threadIdx.x; i < n_inst_total; i += blockDim.x) atomicAdd(&s_hist[63 - min(items_of(i), 63)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < 64; ++k) { s_cursor[k] = run; run += s_hist[k]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_inst_total; i += blockDim.x) {
+        const int b = items_of(i);
+        const int p = atomicAdd(&s_cursor[63 - min(b, 63)], 1);
+        item_inst[p] = i;
+        item_off[p] = b;                  // count for now, prefix below
+    }
+    if (threadIdx.x == 0) s_ca = 0;
+    __syncthreads();
+    for (int base = 0; base < n_inst_total; base += blockDim.x) {
+        const int p = base + threadIdx.x;
+        const long long a = p < n_inst_total ? item_off[p] : 0;
+        long long ia = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long ua = __shfl_up_sync(0xffffffffu, ia, o);
+            if (lane >= (unsigned)o) ia += ua;
+        }
+        if (lane == 31) s_wa[warp] = ia;
+        __syncthreads();
+        long long oa = s_ca;
+        for (unsigned w = 0; w < warp; ++w) oa += s_wa[w];
+        if (p < n_inst_total) item_off[p] = (int32_t)(oa + ia - a);
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_ca = oa + ia;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) item_off[n_inst_total] = (int32_t)s_ca;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -666,14 +696,14 @@ extern "C" int cm3d_scan_segments(const int32_t *tile_cnt, const uint16_t *tile_
                                   const int32_t *frame_desc, int n_frames, int max_inst_per_frame,
                                   int n_inst_total, const int32_t *inst_desc, int64_t seg_cap,
                                   int32_t *tile_prefix, int32_t *frame_n, int32_t *tile_inst_base,
-                                  int32_t *seg_off, int32_t *item_off, unsigned long long *medoid_best,
-                                  int32_t *errflags, void *stream)
+                                  int32_t *seg_off, int32_t *item_off, int32_t *item_inst,
+                                  unsigned long long *medoid_best, int32_t *errflags, void *stream)
 {
     if (n_frames < 0 || max_inst_per_frame < 0 || n_inst_total < 0 || seg_cap < 0) return CM3D_EINVAL;
     if (max_inst_per_frame > CM3D_MAX_INST) return CM3D_ELIMIT;
     if (n_frames == 0) return CM3D_OK;
     if (!tile_cnt || !tile_inst_cnt || !frame_desc || !tile_prefix || !frame_n || !tile_inst_base || !seg_off ||
-        !item_off || !medoid_best || !errflags || (n_inst_total && !inst_desc))
+        !item_off || !item_inst || !medoid_best || !errflags || (n_inst_total && !inst_desc))
         return CM3D_EINVAL;
     // seg_count is staged in seg_off[1..] (k_scan_batch reads element i before writing it)
     int32_t *seg_count = seg_off + 1;
@@ -682,7 +712,7 @@ extern "C" int cm3d_scan_segments(const int32_t *tile_cnt, const uint16_t *tile_
                                                         tile_inst_base, seg_count);
     CM3D_LAUNCH_CHECK();
     k_scan_batch<<<1, 1024, 0, (cudaStream_t)stream>>>(seg_count, inst_desc, frame_desc, n_inst_total, seg_cap,
-                                                       seg_off, item_off, medoid_best, errflags);
+                                                       seg_off, item_off, item_inst, medoid_best, errflags);
     CM3D_LAUNCH_CHECK();
     return CM3D_OK;
 }

@@ -168,10 +168,11 @@ class Lifter:
 
         # ---- scans, ordered compaction + gather
         medoid_best = torch.empty(max(I, 1), dtype=torch.int64, device=dev)
+        item_inst = torch.empty(max(I, 1), **i32)
         self._call("scan", "cm3d_scan_segments", _ptr(tile_cnt), _ptr(tile_inst_cnt), _ptr(db.tab("frame_desc")), F,
                pb.max_inst_per_frame, I, _ptr(inst_desc), seg_cap, _ptr(tile_prefix), _ptr(o("frame_n")),
-               _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(o("item_off")), _ptr(medoid_best),
-               _ptr(o("errflags")), st)
+               _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(o("item_off")), _ptr(item_inst),
+               _ptr(medoid_best), _ptr(o("errflags")), st)
         self.launches += 2
         seg_point_idx = torch.empty(seg_cap, **i32)
         seg_xyzw = torch.empty(4 * seg_cap, dtype=torch.float32, device=dev)
@@ -185,9 +186,9 @@ class Lifter:
         # ---- medoid
         col_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if want_col_sums else None
         if do_medoid and I:
-            max_items = seg_cap // MEDOID_COLS + I
+            max_items = seg_cap // MEDOID_COLS + 2 * I
             self._call("medoid", "cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), _ptr(seg_point_idx),
-                   _ptr(o("item_off")), I, max_items, _ptr(medoid_best), _ptr(col_sums), _ptr(o("medoid_local")),
+                   _ptr(o("item_off")), _ptr(item_inst), I, max_items, _ptr(medoid_best), _ptr(col_sums), _ptr(o("medoid_local")),
                    _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
             self.launches += 2
         # ---- KITTI: principal-axes box + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479)

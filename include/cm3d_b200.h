@@ -48,11 +48,11 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 3
+#define CM3D_ABI_VERSION 4
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
-#define CM3D_MEDOID_COLS 256    /* columns of the distance matrix per medoid work item */
+#define CM3D_MEDOID_COLS 256    /* columns of the distance matrix per full medoid work item */
 
 enum {
     CM3D_OK = 0,
@@ -141,15 +141,16 @@ int cm3d_project_membership(const float *xyzw, const int32_t *tile_cnt, const in
 /* Scans.  tile_prefix[t] = index in the frame's aggr_pc_points of tile t's first point;
  * frame_n[f] = N of frame f; tile_inst_base = exclusive prefix of tile_inst_cnt over the
  * frame's tiles (same layout, int32); seg_off[n_inst_total+1] = exclusive prefix of the
- * per-instance member counts; item_off[n_inst_total+1] = exclusive prefix of the medoid
- * work items (ceil(M/CM3D_MEDOID_COLS) for instances with M >= the frame's minimum, else 0);
- * medoid_best is reset.  Sets errflags[CM3D_ERR_SEG_OVERFLOW] when seg_off[end] > seg_cap. */
+ * per-instance member counts.  Medoid schedule: item_inst[n_inst_total] = the instances ordered
+ * by work-item count, largest first; item_off[n_inst_total+1] = exclusive prefix of
+ * cm3d_medoid_items(M, frame minimum) in that order.  medoid_best is reset.
+ * Sets errflags[CM3D_ERR_SEG_OVERFLOW] when seg_off[end] > seg_cap. */
 int cm3d_scan_segments(const int32_t *tile_cnt, const uint16_t *tile_inst_cnt,
                        const int32_t *frame_desc, int n_frames, int max_inst_per_frame,
                        int n_inst_total, const int32_t *inst_desc, int64_t seg_cap,
                        int32_t *tile_prefix, int32_t *frame_n, int32_t *tile_inst_base,
-                       int32_t *seg_off, int32_t *item_off, unsigned long long *medoid_best,
-                       int32_t *errflags, void *stream);
+                       int32_t *seg_off, int32_t *item_off, int32_t *item_inst,
+                       unsigned long long *medoid_best, int32_t *errflags, void *stream);
 
 /* Ordered (ascending point index) per-instance index lists + gathered points.
  * seg_xyzw: 4 arrays of seg_cap floats.  Does nothing when the overflow flag is set. */
@@ -169,12 +170,18 @@ int cm3d_compact_segments(const float *xyzw, const int32_t *tile_cnt, const int3
  * (-1 if the instance has fewer than its frame's minimum points); medoid_point_idx = that
  * point's index in aggr_pc_points; centroid[4*i..] = its x,y,z,4th row (NaN when absent).
  * col_sums (optional, seg_cap floats) receives every column sum.  max_items bounds the grid:
- * it must be >= item_off[n_inst_total] (seg_cap/CM3D_MEDOID_COLS + n_inst_total always is). */
+ * it must be >= item_off[n_inst_total] (seg_cap/CM3D_MEDOID_COLS + 2*n_inst_total always is).
+ * item_off / item_inst: the schedule written by cm3d_scan_segments. */
 int cm3d_medoid(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off,
-                const int32_t *seg_point_idx, const int32_t *item_off, int n_inst_total,
+                const int32_t *seg_point_idx, const int32_t *item_off, const int32_t *item_inst,
+                int n_inst_total,
                 int max_items, unsigned long long *medoid_best, float *col_sums,
                 int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
                 const int32_t *errflags, void *stream);
+
+/* Work items of an instance with m member points (host helper; 0 below min_pts, 1 below 32 points,
+ * else ceil(floor32(m)/CM3D_MEDOID_COLS) full items + one tail item when m % 32 != 0). */
+int cm3d_medoid_items(int m, int min_pts);
 
 /* ---- KITTI orientation (PARITY UNPINNED: open3d is not in the reference tree) ------------------ */
 

@@ -125,13 +125,13 @@ def test_small_segments_all_sizes(lifter):
     import torch, ctypes
     from cm3d_b200 import _native as N
     rng = np.random.default_rng(0)
-    sizes = list(range(1, 71)) + [95, 96, 97, 255, 256, 257, 1023, 1025]
+    sizes = list(range(1, 71)) + [95, 96, 97, 255, 256, 257, 287, 288, 289, 1023, 1024, 1025, 2077]
     pts = [(rng.normal(0, 3, (3, m)) + np.array([[1200.0], [950.0], [1.0]])).astype(np.float32) for m in sizes]
     seg_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     cap = int(seg_off[-1] + 3) & ~3
     xyzw = np.zeros((4, cap), np.float32)
     xyzw[:3, :seg_off[-1]] = np.concatenate(pts, 1)
-    items = [-(-m // 256) for m in sizes]
+    items = [N.load().cm3d_medoid_items(int(m), 1) for m in sizes]
     item_off = np.concatenate([[0], np.cumsum(items)]).astype(np.int32)
     dev = "cuda:0"
     t = lambda a: torch.from_numpy(a).to(dev)
@@ -145,7 +145,8 @@ def test_small_segments_all_sizes(lifter):
     cen = torch.zeros(4 * n, dtype=torch.float32, device=dev)
     err = torch.zeros(4, dtype=torch.int32, device=dev)
     p = lambda x: ctypes.c_void_p(x.data_ptr())
-    N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), n, int(item_off[-1]) + 3, p(best), p(col),
+    d_inst = torch.arange(n, dtype=torch.int32, device=dev)
+    N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), p(d_inst), n, int(item_off[-1]) + 3, p(best), p(col),
            p(ml), p(mp), p(cen), p(err), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     col, ml = col.cpu().numpy(), ml.cpu().numpy()
