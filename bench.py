@@ -202,6 +202,17 @@ def run_ours(args, rank, world, local_rank):
     final = lifter.fetch_labels(do)
     assert lifter.check_flags(final) == 0
 
+    # ---- host->device copy rate of one packed batch (explains e2e when PCIe, not the kernels, bounds it)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lifter.upload(pb)
+    torch.cuda.synchronize()
+    h0.record()
+    for _ in range(3):
+        lifter.upload(pb)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * pb.h2d_bytes / (h0.elapsed_time(h1) * 1e-3) / 1e9
+
     # ---- end to end: pinned host buffers -> H2D -> kernels -> D2H of the labels, every step
     for lab in lifter.lift_packed_stream([pb] * 3, seg_cap=seg_cap):
         pass
@@ -262,7 +273,8 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": f"frames sharded by sample index, {world} process(es), no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pb.h2d_bytes * world,
-                    "d2h_bytes_per_step": int(do.out.numel() * 4) * world, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(do.out.numel() * 4) * world, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_gbps_rank0": round(h2d_gbps, 1)},
             "gpu_launches": launches,
             "roofline": roof,
             "kernels": kern,

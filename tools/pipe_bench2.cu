@@ -155,6 +155,85 @@ __global__ void kmed(float *out, const float4 *rows_g, float xj, float yj, float
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// Column-packed step: every packed op handles (column c0, column c1) of ONE row; rows in shared
+// memory with duplicated halves: s_rows[2r] = (X,X,Y,Y), s_rows[2r+1] = (Z,Z,W,W).  NCP column pairs/thread.
+template <int NCP, int ROWS>
+__global__ void kmedc(float *out, const float4 *rows_g, float xj, float yj, float zj, float nnj)
+{
+    __shared__ float4 s_rows[2 * ROWS];
+    for (int i = threadIdx.x; i < 2 * ROWS; i += blockDim.x) s_rows[i] = rows_g[i];
+    __syncthreads();
+    u64 xj2[NCP], yj2[NCP], zj2[NCP], nj2[NCP], a0[NCP];
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) {
+        const float o = (float)(threadIdx.x + c * 256);
+        xj2[c] = pk(xj + o, xj + o + 0.5f); yj2[c] = pk(yj, yj + 1.f); zj2[c] = pk(zj, zj); nj2[c] = pk(nnj - 2400.f * o, nnj - 2400.f * o - 1200.f);
+        a0[c] = pk(0.f, 0.f);
+    }
+    for (int it = 0; it < 64 * (1024 / ROWS); ++it) {
+        for (int b = 0; b < ROWS; b += 8) {
+            u64 nd[NCP][8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 a = s_rows[2 * (b + q)], bb = s_rows[2 * (b + q) + 1];
+#pragma unroll
+                for (int c = 0; c < NCP; ++c) {
+                    u64 nr = mul2(pk(a.x, a.y), xj2[c]);
+                    nr = fma2(pk(a.z, a.w), yj2[c], nr);
+                    nr = fma2(pk(bb.x, bb.y), zj2[c], nr);
+                    nr = add2(pk(bb.z, bb.w), nr);
+                    nr = add2(nj2[c], nr);
+                    float n0, n1, y0, y1;
+                    upk(nr, n0, n1);
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(-n0));
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(-n1));
+                    const u64 y = pk(y0, y1);
+                    const u64 ns = mul2(nr, y);
+                    const u64 h = mul2(y, pk(0.5f, 0.5f));
+                    const u64 rr = fma2(ns, ns, nr);
+                    float d0, d1;
+                    upk(fma2(rr, h, ns), d0, d1);
+                    nd[c][q] = pk(fminf(d0, -0.0f), fminf(d1, -0.0f));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int c = 0; c < NCP; ++c) asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(a0[c]) : "l"(nd[c][q]));
+        }
+    }
+    float s = 0;
+    for (int c = 0; c < NCP; ++c) { float lo, hi; upk(a0[c], lo, hi); s += lo + hi; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int NCP, int ROWS> void runmedc(const char *name, int blocks_per_sm, int threads)
+{
+    float *d; cudaMalloc(&d, 148 * 16 * 1024 * 4);
+    float4 *rows; cudaMalloc(&rows, 2 * ROWS * 16);
+    float4 *h = new float4[2 * ROWS];
+    for (int i = 0; i < ROWS; ++i) {
+        const float x0 = 1200 + i * 0.01f, y0 = 950.f, z0 = 1.f;
+        const float n0 = x0 * x0 + y0 * y0 + z0 * z0;
+        h[2 * i] = make_float4(2 * x0, 2 * x0, 2 * y0, 2 * y0);
+        h[2 * i + 1] = make_float4(2 * z0, 2 * z0, -n0, -n0);
+    }
+    cudaMemcpy(rows, h, 2 * ROWS * 16, cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const float nj = 1200.f * 1200.f + 950.f * 950.f + 1.f;
+    kmedc<NCP, ROWS><<<148 * blocks_per_sm, threads>>>(d, rows, 1200.f, 950.f, 1.f, -nj);
+    cudaEventRecord(e0);
+    kmedc<NCP, ROWS><<<148 * blocks_per_sm, threads>>>(d, rows, 1200.f, 950.f, 1.f, -nj);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double cyc = ms * 1e-3 * 1.965e9;
+    double warp_rows_per_smsp = (blocks_per_sm * threads / 32 / 4.0) * 64.0 * 1024 * NCP * 2;
+    cudaError_t err = cudaGetLastError();
+    printf("%-40s NCP=%d rows/tile=%d %d blk/SM x %d thr: %.3f ms -> %.2f cycles per warp-row-col per SMSP %s\n", name, NCP, ROWS, blocks_per_sm, threads, ms,
+           cyc / warp_rows_per_smsp, err == cudaSuccess ? "" : cudaGetErrorString(err));
+    cudaFree(d); cudaFree(rows);
+}
+
 template <int VAR, int NC> void runmed(const char *name, int blocks_per_sm, int threads)
 {
     float *d; cudaMalloc(&d, 148 * 16 * 1024 * 4);
@@ -207,5 +286,8 @@ int main()
     runmed<1, 4>("NaN-cleanup packed", 4, 128);
     runmed<2, 1>("NaN-cleanup scalar", 4, 256); runmed<2, 2>("NaN-cleanup scalar", 4, 128);
     runmed<3, 2>("scalar chain, packed sqrt", 4, 128); runmed<4, 2>("packed chain, scalar sqrt", 4, 128);
+    runmedc<1, 512>("column-packed", 4, 256); runmedc<1, 512>("column-packed", 7, 128); runmedc<1, 512>("column-packed", 8, 128);
+    runmedc<2, 512>("column-packed", 4, 128); runmedc<2, 512>("column-packed", 7, 128); runmedc<2, 512>("column-packed", 7, 64); runmedc<2, 512>("column-packed", 14, 64);
+    runmedc<1, 1024>("column-packed", 6, 128);
     return 0;
 }
