@@ -20,6 +20,7 @@ _L = ctypes.c_int64
 # name -> argtypes (restype is int for all but the two listed below); mirrors include/cm3d_b200.h
 PROTOTYPES = {
     "cm3d_masks_pack_dense": [_P, _P, _P, _I, _I, _P, _P],
+    "cm3d_masks_decode_counts": [_P, _P, _I, _P, _P],
     "cm3d_masks_fill_rle": [_P, _P, _P, _P, _I, _I, _P, _P, _P],
     "cm3d_masks_erode3x3": [_P, _P, _I, _I, _P, _P, _P],
     "cm3d_aggregate_sweeps": [_P, _P, _I, _P, _P, _P, _P, _P, _P],
@@ -30,6 +31,7 @@ PROTOTYPES = {
     "cm3d_medoid": [_P, _L, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "cm3d_medoid_items": [_I, _I],
     "cm3d_pca_obb": [_P, _L, _P, _I, _I, _P, _P, _P],
+    "cm3d_nearest_lane": [_P, _I, _P, _I, _P, _P, _P],
     "cm3d_selftest_sqrt": [_P, _P],
 }
 EXPORTS = ["cm3d_abi_version", "cm3d_error_string"] + list(PROTOTYPES)

@@ -63,11 +63,11 @@ class PackedBatch:
     bits_words: int                 # total words of one set of bit planes
     max_words: int                  # largest single plane
     n_raw_points: int
-    masks_kind: str                 # "dense" | "rle"
+    masks_kind: str                 # "dense" | "rle" (uint32 runs) | "rle_str" (pycocotools counts bytes)
     max_runs: int
     raw: np.ndarray                 # float32
     meta: np.ndarray                # int32
-    mask: np.ndarray                # uint8 (dense bytes) or uint32 (runs)
+    mask: np.ndarray                # uint8 (dense bytes / counts strings) or uint32 (runs)
     mask_off: np.ndarray            # int64: src_off[n_inst] or run_off[n_inst+1]
     off: Dict[str, int] = field(default_factory=dict)       # table name -> int32 offset in meta
     frame_inst: np.ndarray = None   # (F+1,) instance ranges
@@ -91,8 +91,13 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
     F = len(frames)
     if F == 0:
         raise ValueError("empty batch")
-    kinds = {("dense" if isinstance(f.masks, np.ndarray) else "rle") for f in frames if f.n_instances}
-    masks_kind = "dense" if kinds == {"dense"} else "rle"
+    def _kind(f):
+        if isinstance(f.masks, np.ndarray):
+            return "dense"
+        return "rle_str" if all(isinstance(m.counts, (bytes, str)) for m in f.masks) else "rle"
+    kinds = {_kind(f) for f in frames if f.n_instances}
+    # dense uint8 | pycocotools `counts` strings (decoded on the GPU) | uint32 run lengths
+    masks_kind = kinds.pop() if len(kinds) == 1 else "rle"
 
     # ---- geometry pass
     n_sweeps = sum(len(f.sweeps) for f in frames)
@@ -192,6 +197,12 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
                     raise ValueError("dense mask shape mismatch")
                 mask_chunks.append(np.ascontiguousarray(m, np.uint8).reshape(-1))
                 mask_off.append(mask_off[-1] + ((H * W + 15) & ~15))
+            elif masks_kind == "rle_str":
+                c = f.masks[i].counts
+                c = np.frombuffer(c.encode("ascii") if isinstance(c, str) else c, np.uint8)
+                mask_chunks.append(c)
+                mask_off.append(mask_off[-1] + len(c))
+                max_runs = max(max_runs, len(c))
             else:
                 rle = f.masks[i]
                 if isinstance(f.masks, np.ndarray):
@@ -210,7 +221,7 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
             mask[o:o + c.size] = c
         mask_off_arr = np.asarray(mask_off[:-1] if n_inst else [0], np.int64)
     else:
-        mask, mask_t = _alloc(mask_off[-1], np.uint32, pin)
+        mask, mask_t = _alloc(mask_off[-1], np.uint8 if masks_kind == "rle_str" else np.uint32, pin)
         if mask_chunks:
             np.concatenate(mask_chunks, out=mask[:mask_off[-1]])
         mask_off_arr = np.asarray(mask_off, np.int64)

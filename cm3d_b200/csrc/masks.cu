@@ -45,6 +45,83 @@ k_pack_dense(const uint8_t *__restrict__ masks, const int64_t *__restrict__ src_
 }
 
 // ------------------------------------------------------------------ COCO runs -> bits
+// ------------------------------------------------------------------ COCO `counts` string -> runs
+// pycocotools' compressed run lengths (maskApi.c rleFrString, restated in cm3d_b200/rle.py): every
+// run is 1..7 chars of 5 payload bits (char - 48; bit 0x20 = "more", sign-extended from bit 0x10
+// of the last char); from the 4th run on the value is a delta against the run two places back.
+// One block per instance.  Pass 1: every char that starts a token decodes it (tokens are found
+// with a ballot prefix over "previous char ended a token").  Pass 2: the deltas are two
+// interleaved running sums (odd tokens from token 1, even tokens from token 2), done as a block
+// scan over token pairs.  Instance i's runs land at runs[byte_off[i] ..), zero-padded up to
+// byte_off[i+1] (a run never needs less than one char), so run_off == byte_off downstream.
+__global__ void __launch_bounds__(256)
+k_rle_decode(const uint8_t *__restrict__ bytes, const int64_t *__restrict__ byte_off, uint32_t *__restrict__ runs)
+{
+    __shared__ uint32_t s_a[8], s_b[8];
+    __shared__ uint32_t s_ca, s_cb;
+    const int i = blockIdx.x;
+    const int64_t b0 = byte_off[i];
+    const int nb = (int)(byte_off[i + 1] - b0);
+    const uint8_t *src = bytes + b0;
+    uint32_t *dst = runs + b0;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_ca = 0; s_cb = 0; }
+    __syncthreads();
+    for (int base = 0; base < nb; base += blockDim.x) {
+        const int p = base + threadIdx.x;
+        const bool start = p < nb && (p == 0 || !((src[p - 1] - 48) & 0x20));
+        const unsigned bal = __ballot_sync(0xffffffffu, start);
+        if (lane == 0) s_a[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t t = s_ca + __popc(bal & lanemask_lt());
+        for (unsigned w = 0; w < warp; ++w) t += s_a[w];
+        if (start) {
+            long long x = 0;
+            int k = 0, q = p;
+            bool more = true;
+            while (more && q < nb) {
+                const int c = (int)src[q] - 48;
+                x |= (long long)(c & 0x1f) << (5 * k);
+                more = (c & 0x20) != 0;
+                ++q; ++k;
+                if (!more && (c & 0x10)) x |= -1ll << (5 * k);
+            }
+            dst[t] = (uint32_t)x;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; ++w) tot += s_a[w];
+            s_ca += tot;
+        }
+        __syncthreads();
+    }
+    const int ntok = (int)s_ca;
+    for (int t = ntok + threadIdx.x; t < nb; t += blockDim.x) dst[t] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) s_ca = 0;
+    __syncthreads();
+    for (int base = 0; 2 * base < ntok; base += blockDim.x) {
+        const int te = 2 * (base + threadIdx.x), to = te + 1;
+        const bool he = te < ntok && te >= 2, ho = to < ntok;
+        uint32_t e = he ? dst[te] : 0u, o = ho ? dst[to] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ue = __shfl_up_sync(0xffffffffu, e, d), uo = __shfl_up_sync(0xffffffffu, o, d);
+            if (lane >= (unsigned)d) { e += ue; o += uo; }
+        }
+        if (lane == 31) { s_a[warp] = e; s_b[warp] = o; }
+        __syncthreads();
+        uint32_t ce = s_ca, co = s_cb;
+        for (unsigned w = 0; w < warp; ++w) { ce += s_a[w]; co += s_b[w]; }
+        if (he) dst[te] = ce + e;
+        if (ho) dst[to] = co + o;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) { s_ca = ce + e; s_cb = co + o; }
+        __syncthreads();
+    }
+}
+
 // run_start[r] = first flat pixel (y*W + x) of run r; one block per instance.
 __global__ void __launch_bounds__(256)
 k_rle_prefix(const uint32_t *__restrict__ runs, const int64_t *__restrict__ run_off,
@@ -198,6 +275,17 @@ extern "C" int cm3d_masks_pack_dense(const uint8_t *masks, const int64_t *src_of
     if (!masks || !src_off || !inst_desc || !bits) return CM3D_EINVAL;
     dim3 grid((max_words + 255) / 256, n_inst);
     k_pack_dense<<<grid, 256, 0, (cudaStream_t)stream>>>(masks, src_off, inst_desc, bits);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}
+
+extern "C" int cm3d_masks_decode_counts(const uint8_t *counts, const int64_t *byte_off, int n_inst,
+                                        uint32_t *runs, void *stream)
+{
+    if (n_inst < 0) return CM3D_EINVAL;
+    if (n_inst == 0) return CM3D_OK;
+    if (!counts || !byte_off || !runs) return CM3D_EINVAL;
+    k_rle_decode<<<n_inst, 256, 0, (cudaStream_t)stream>>>(counts, byte_off, runs);
     CM3D_LAUNCH_CHECK();
     return CM3D_OK;
 }

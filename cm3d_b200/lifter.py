@@ -133,8 +133,13 @@ class Lifter:
                 self.launches += 1
             else:
                 bits_raw.zero_()
-                run_start = torch.empty(max(db.mask.numel(), 1), **i32)
-                self._call("masks_rle", "cm3d_masks_fill_rle", _ptr(db.mask), _ptr(db.mask_off), _ptr(run_start), _ptr(inst_desc),
+                runs = db.mask
+                if pb.masks_kind == "rle_str":      # pycocotools counts strings -> run lengths on the device
+                    runs = torch.empty(max(db.mask.numel(), 1), **i32)
+                    self._call("masks_decode", "cm3d_masks_decode_counts", _ptr(db.mask), _ptr(db.mask_off), I, _ptr(runs), st)
+                    self.launches += 1
+                run_start = torch.empty(max(runs.numel(), 1), **i32)
+                self._call("masks_rle", "cm3d_masks_fill_rle", _ptr(runs), _ptr(db.mask_off), _ptr(run_start), _ptr(inst_desc),
                        I, pb.max_runs, _ptr(bits_raw), _ptr(o("errflags")), st)
                 self.launches += 3
             self._call("masks_erode", "cm3d_masks_erode3x3", _ptr(bits_raw), _ptr(inst_desc), I, pb.max_words, _ptr(bits),
@@ -226,7 +231,33 @@ class Lifter:
         res["centroid"] = res["centroid"].view(np.float32).reshape(-1, 4)
         return res
 
-    def lift_packed_stream(self, batches, seg_cap: Optional[int] = None, depth: int = 2):
+    def lift_frame_stream(self, frames, batch_frames: int = 32, timer: Optional[dict] = None, depth: int = 2):
+        """Drop-in scripts' entry: an iterator of FrameSpecs in, lists of LiftResult (one list per
+        batch of `batch_frames` frames, frame order kept) out.  Batches are packed into pinned
+        buffers and pipelined through `lift_packed_stream`; per-instance point lists stay on the
+        device (the scripts only need sizes, medoids, centroids and the KITTI yaw).  `timer`, when
+        given, gets the wall time spent here under the reference's "points in mask" key."""
+        import time
+
+        def batches():
+            cur = []
+            for f in frames:
+                cur.append(f)
+                if len(cur) >= batch_frames:
+                    yield self.pack(cur)
+                    cur = []
+            if cur:
+                yield self.pack(cur)
+
+        t0 = time.time()
+        for pb, do, lab in self.lift_packed_stream(batches(), depth=depth, with_handles=True):
+            res = self.results(do, lab, with_points=False)
+            if timer is not None:
+                timer["points in mask"] += time.time() - t0
+            yield res
+            t0 = time.time()
+
+    def lift_packed_stream(self, batches, seg_cap: Optional[int] = None, depth: int = 2, with_handles: bool = False):
         """Pipelined bulk path (config C5: tens of thousands of frames): yields the label dict of
         every PackedBatch in order.  Batch k+1 is copied host->device on a copy stream while batch
         k runs on the compute stream; the small result block comes back asynchronously into
@@ -244,11 +275,11 @@ class Lifter:
             need = self.check_flags(lab)
             if need:                        # rare: rerun this batch synchronously with exact capacity
                 with torch.cuda.stream(comp_s):
-                    do2 = self.run(db, seg_cap=need)
-                    lab = self.fetch_labels(do2)
+                    do = self.run(db, seg_cap=need)
+                    lab = self.fetch_labels(do)
                 if self.check_flags(lab):
                     raise N.Cm3dError("segment capacity retry failed")
-            return lab
+            return (pb, do, lab) if with_handles else lab
 
         for pb in batches:
             with torch.cuda.stream(copy_s):

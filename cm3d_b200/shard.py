@@ -18,6 +18,22 @@ def world_from_env():
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
+def init_distributed():
+    """(rank, world, local_rank); under torchrun (WORLD_SIZE > 1) also makes sure a process group
+    exists for the host-side label gather (gloo: the gather moves pickled label dicts, not tensors)."""
+    rank, world, local_rank = world_from_env()
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def stage_device(cfg_device: str, world: int, local_rank: int) -> str:
+    """One process per GPU: under torchrun rank r lifts on cuda:<LOCAL_RANK>, else on the script's DEVICE."""
+    return f"cuda:{local_rank}" if world > 1 else cfg_device
+
+
 def shard_indices(n: int, rank: int, world: int, mode: str = "interleaved") -> List[int]:
     """Sample indices owned by `rank`.  "interleaved": i -> rank i mod G (even load when frame
     cost varies slowly with time); "blocked": contiguous blocks (keeps a scene's frames together)."""

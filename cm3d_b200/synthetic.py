@@ -385,6 +385,14 @@ def make_waymo_frame(seed, n_pts=180000, n_inst=80, mask_div=1, obj_frac=0.30,
 
 
 # ----------------------------------------------------------------------------- RLE helpers
+def compress_rles(rles):
+    """RLEMasks with uint32 run arrays -> RLEMasks with pycocotools' compressed `counts` bytes,
+    the on-disk format of {f}_masks.pkl (gen_2d_masks_detic.py:471,506)."""
+    from .frames import RLEMask
+    from .rle import rle_counts_to_runs, runs_to_rle_string
+    return [RLEMask(r.size, runs_to_rle_string(rle_counts_to_runs(r.counts))) for r in rles]
+
+
 def dense_to_rle(masks_hw: np.ndarray):
     """(I,H,W) uint8 -> list[RLEMask] with uncompressed uint32 counts.
 

@@ -1,0 +1,243 @@
+"""Waymo lifting stage: the `__main__` of the reference's src/waymo/2d_to_3d.py as a function, the
+per-frame / per-mask body replaced by the CUDA path.
+
+Follows src/waymo/2d_to_3d.py:395-1305.  Pass 1 per frame (:445-702): masks + data (missing files
+skip the frame, :450-455), lanes with finite-difference yaws from frame 0's map features
+(:459-468 -> :374-388), TOP-LiDAR first-return points + a ones row in the vehicle frame (:472-481);
+per mask: camera `c + 1` (:513-518), extrinsic . inv(axes) -> scipy quaternion -> pyquaternion
+matrix (:557-575), intrinsics x 1024/1920 in fp64 (:586-593), membership, medoid (:649-653),
+centroid to the global frame through `frame.pose` (:684-699).  Closest lane per centroid (:751).
+Pass 2 (:785-870): back to the vehicle frame with inv(pose), shape prior, lane-aligned heading,
+push-back, `metrics_pb2.Object`; per-timestamp circle NMS (:1108-1275); serialised Objects file
+(:1300-1305).
+
+`scenes` is an iterable of (scene_name, frames); frames are `dataset_pb2.Frame`s or duck-typed
+equivalents.  `points_fn(frame)` returns the (N,3) vehicle-frame points; the default parses the
+range images with waymo_open_dataset exactly like the reference.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from types import SimpleNamespace
+from typing import Callable, Iterable, List, Optional
+
+import numpy as np
+
+from . import boxes as B
+from . import waymo_proto as WP
+from .frames import CamSpec, FrameSpec, FOURTH_ONES, op_R, op_T
+from .nuscenes_stage import load_frame_masks, new_timer
+from .quat import Quaternion
+
+DEFAULTS = dict(
+    INPUT_PATH="../../data/waymo/training/", OUTPUT_DIR="../../outputs/waymo/",
+    INPUT_DIR="../../mask_outputs/waymo-detic/", ATTRIBUTE_NAMES=B.ATTRIBUTE_NAMES, DEVICE="cuda:0",
+    CAM_LIST=["FRONT", "FRONT_LEFT", "FRONT_RIGHT", "SIDE_LEFT", "SIDE_RIGHT"],
+    min_dist=2.3, floor_thresh=-0.6, ratio=1024 / 1920, scene_slice=(680, 710),
+    shape_priors_path="cfg/shape_priors_chatgpt.json", output_path="../../outputs/waymo/pred_0307_detic_train_680_710.bin",
+    batch_frames=32,
+)
+WAYMO_THRESHS = {WP.TYPE_UNKNOWN: 1, WP.TYPE_SIGN: 0.175, WP.TYPE_CYCLIST: 0.85, WP.TYPE_PEDESTRIAN: 0.175,
+                 WP.TYPE_VEHICLE: 4}          # waymo:1119-1125
+
+
+def make_cfg(**overrides) -> SimpleNamespace:
+    d = dict(DEFAULTS)
+    d.update(overrides)
+    return SimpleNamespace(**d)
+
+
+def get_yaws_from_lane_coords(lane_list) -> np.ndarray:
+    """waymo:374-388: yaw of each polyline vertex from the step to it; vertex 0 copies vertex 1."""
+    prev_x, prev_y = 0, 0
+    out = []
+    for xyz in lane_list:
+        x, y = xyz.x, xyz.y
+        out.append([x, y, np.arctan2(y - prev_y, x - prev_x)])
+        prev_x, prev_y = x, y
+    if len(out) > 1:
+        out[0][2] = out[1][2]
+    return np.array(out)
+
+
+def lanes_of_frame(frame) -> np.ndarray:
+    lane_pt_list = []
+    for feature in frame.map_features:                                   # waymo:461-468
+        if feature.HasField("lane"):
+            lane_pt_list.append(get_yaws_from_lane_coords(list(feature.lane.polyline)))
+    return np.vstack(lane_pt_list)
+
+
+def default_points_fn(frame) -> np.ndarray:
+    from waymo_open_dataset.utils import frame_utils                     # waymo:472-476
+    range_images, camera_projections, _, range_image_top_pose = frame_utils.parse_range_image_and_camera_projection(frame)
+    point_clouds, _ = frame_utils.convert_range_image_to_point_cloud(frame, range_images, camera_projections,
+                                                                     range_image_top_pose, 0, False)
+    return point_clouds[0]
+
+
+def _wxyz_of_matrix32(rot32):
+    """`quat = R.from_matrix(rotation_matrix.cpu()); rotation = (q[3], q[0], q[1], q[2])` (waymo:568-571)."""
+    from scipy.spatial.transform import Rotation as R
+    q = R.from_matrix(np.asarray(rot32)).as_quat()
+    return (q[3], q[0], q[1], q[2])
+
+
+def cam_spec(cam_calib, ratio: float) -> CamSpec:
+    import torch
+    axes = torch.Tensor([[0, -1, 0, 0], [0, 0, -1, 0], [1, 0, 0, 0], [0, 0, 0, 1]]).to(dtype=torch.float32)
+    axes = torch.linalg.inv(axes)                                        # waymo:557-562
+    tm = torch.from_numpy(np.array(cam_calib.extrinsic.transform).reshape(4, 4)).to(dtype=torch.float32)
+    tm = torch.matmul(tm, axes)
+    rotation = _wxyz_of_matrix32(tm[:3, :3].numpy())
+    t = (-tm[:3, 3]).numpy()                                             # cam_pc.translate(-T[:3,3])
+    Rt = np.asarray(Quaternion(rotation).rotation_matrix.T, np.float64).astype(np.float32)
+    matrix = np.array(cam_calib.intrinsic, np.float32).tolist()          # waymo:586-593: fp64 maths, then cast
+    K = np.array([[matrix[0], 0, matrix[2]], [0, matrix[1], matrix[3]], [0, 0, 1]]) * ratio
+    K[2, 2] = 1
+    return CamSpec([op_T(t), op_R(Rt)], K.astype(np.float32))
+
+
+def frame_spec(frame, masks, data, cfg, points_fn: Callable) -> FrameSpec:
+    pts = np.ascontiguousarray(np.asarray(points_fn(frame))[:, :3], np.float32)
+    by_name = {int(c.name): c for c in frame.context.camera_calibrations}
+    n = len(data["labels"])
+    cam_nums = [int(c) for c in data["cam_nums"][:n]]
+    for c in cam_nums:
+        if c + 1 not in by_name:
+            print("Invalid cam_num")                                     # waymo:516-518
+            raise SystemExit
+    used = sorted(set(cam_nums))
+    cams = [cam_spec(by_name[c + 1], cfg.ratio) for c in used]
+    remap = {c: k for k, c in enumerate(used)}
+    return FrameSpec("waymo", [pts], [[]], cams if cams else [CamSpec([], np.eye(3, dtype=np.float32))],
+                     np.asarray([remap[c] for c in cam_nums], np.int32), masks[:n], list(data["labels"]),
+                     list(data["detection_scores"]), fourth=FOURTH_ONES, close_thresh=None, min_dist=cfg.min_dist,
+                     token=f"{frame.context.name}:{frame.timestamp_micros}")
+
+
+def centroid_to_global(centroid_xyz1: np.ndarray, frame) -> np.ndarray:
+    """Vehicle -> global with the reference's fp32 ops (waymo:684-699): rotate by the pyquaternion
+    matrix of the pose rotation, then add the pose translation."""
+    import torch
+    tm = torch.from_numpy(np.array(frame.pose.transform, np.float32).reshape(4, 4)).to(dtype=torch.float32)
+    rotation = _wxyz_of_matrix32(tm[:3, :3].numpy())
+    Rm = torch.from_numpy(Quaternion(rotation).rotation_matrix).to(dtype=torch.float32)
+    p = torch.from_numpy(np.asarray(centroid_xyz1, np.float32).reshape(-1, 1)[:3].copy())
+    p = torch.matmul(Rm, p)                                              # pcd.py rotate
+    for i in range(3):                                                   # pcd.py translate
+        p[i, :] = p[i, :] + tm[i, 3]
+    return p[:3, 0].numpy()
+
+
+def object_of(frame, label: str, score, centroid_global: np.ndarray, global_lane_yaw, shape_priors: dict) -> dict:
+    """Pass 2 for one instance (waymo:803-858) -> a dict with the metrics_pb2.Object fields."""
+    from scipy.spatial.transform import Rotation as R
+    detection_name = B.get_detection_name(label)
+    transform_matrix = np.array(frame.pose.transform, np.float32).reshape(4, 4)
+    transform_matrix = np.linalg.inv(transform_matrix)
+    centroid_pc = np.hstack([np.squeeze(np.array(centroid_global)), [1]])
+    centroid = np.dot(transform_matrix, centroid_pc)[:3]
+    extents = B.get_shape_prior(shape_priors, detection_name, waymo=True)
+    if detection_name in B.VEHICLE_NAMES:
+        global_align_mat = B.lane_align_matrix(global_lane_yaw)
+        align_mat = np.dot(transform_matrix[:3, :3], global_align_mat)
+        pushed = B.push_centroid(centroid, extents, Quaternion(matrix=global_align_mat), ego_frame=True)
+        heading = R.from_matrix(align_mat).as_euler("xyz", degrees=False)[2]
+    else:
+        pushed = centroid
+        heading = R.from_matrix(np.eye(3)).as_euler("xyz", degrees=False)[2]
+    wname = B.NUSC_TO_WAYMO[detection_name]
+    if wname not in WP.TYPE_BY_NAME:
+        raise ValueError(detection_name)                                 # waymo:1060-1061 (barrier / traffic_cone)
+    return {"context_name": frame.context.name, "frame_timestamp_micros": int(frame.timestamp_micros),
+            "center_x": float(pushed[0]), "center_y": float(pushed[1]), "center_z": float(pushed[2]),
+            "length": float(extents[1]), "width": float(extents[0]), "height": float(extents[2]),
+            "heading": float(heading), "score": float(np.float32(float(score))), "type": WP.TYPE_BY_NAME[wname],
+            "id": "unique object tracking ID"}
+
+
+def nms_objects(objects: List[dict]) -> List[dict]:
+    """Per-timestamp circle NMS (waymo:1108-1275)."""
+    by_ts = {}
+    for o in objects:
+        by_ts.setdefault(o["frame_timestamp_micros"], []).append(o)
+    final = []
+    for ts, objs in by_ts.items():
+        dets = np.array([np.array([o["center_x"], o["center_y"], o["score"]]) for o in objs])
+        keep = set(int(k) for k in B.circle_nms(dets, [o["type"] for o in objs], WAYMO_THRESHS))
+        final.extend(o for c, o in enumerate(objs) if c in keep)
+    return final
+
+
+def run(cfg, scenes: Iterable, points_fn: Optional[Callable] = None, lifter=None, write: bool = True) -> List[dict]:
+    from .lifter import Lifter
+    from .shard import gather_labels, init_distributed, stage_device
+    total_start = time.time()
+    timer = new_timer()
+    rank, world, local_rank = init_distributed()
+    cfg.DEVICE = stage_device(cfg.DEVICE, world, local_rank)
+    points_fn = points_fn or default_points_fn
+    lifter = lifter or Lifter(cfg.DEVICE)
+    with open(cfg.shape_priors_path) as f:
+        shape_priors = json.load(f)
+    local = {}
+    n_scenes = 0
+    for scene_num, (scene_name, scene_frames) in enumerate(scenes):
+        n_scenes += 1
+        if scene_num % world != rank:
+            continue
+        kept, lanes = [], [None]                  # (frame, data) of the frames that have mask files
+
+        def frames():
+            for frame_num, frame in enumerate(scene_frames):
+                t0 = time.time()
+                try:
+                    masks, data = load_frame_masks(cfg.INPUT_DIR, scene_name, frame_num)
+                except FileNotFoundError:
+                    continue                                             # waymo:453-455
+                if frame_num == 0:
+                    lanes[0] = lanes_of_frame(frame)
+                spec = frame_spec(frame, masks, data, cfg, points_fn)
+                kept.append((frame, data))
+                timer["io"] += time.time() - t0
+                yield spec
+
+        cents, owners = [], []                    # global centroids, (kept index, instance index)
+        k = 0
+        for res_batch in lifter.lift_frame_stream(frames(), batch_frames=cfg.batch_frames, timer=timer):
+            for r in res_batch:
+                frame, _ = kept[k]
+                for i in range(len(r.medoid_local)):
+                    if r.medoid_local[i] >= 0:
+                        cents.append(centroid_to_global(r.centroids[i], frame))
+                        owners.append((k, i))
+                k += 1
+        objs = []
+        if cents:
+            t0 = time.time()
+            yaw_list, _, _ = B.lane_yaws_distances_and_coords(np.asarray(cents, np.float32), lanes[0], cfg.DEVICE)
+            timer["closest lane"] += time.time() - t0
+            for (k, i), cg, yaw in zip(owners, cents, yaw_list):
+                frame, data = kept[k]
+                objs.append(object_of(frame, data["labels"][i], data["detection_scores"][i], cg, yaw, shape_priors))
+        local[scene_num] = objs
+    merged = gather_labels(local, n_scenes) if world > 1 else [local.get(i) for i in range(n_scenes)]
+    if rank != 0:
+        return []
+    objects = [o for part in merged if part for o in part]
+    print("\nRunning NMS on the predictions.\n")
+    t0 = time.time()
+    final = nms_objects(objects)
+    timer["nms"] += time.time() - t0
+    print(len(final), len(objects))
+    if write:
+        os.makedirs(os.path.dirname(os.path.abspath(cfg.output_path)), exist_ok=True)
+        with open(cfg.output_path, "wb") as f:
+            f.write(WP.serialize_objects(final))
+    timer["total"] += time.time() - total_start
+    for operation in timer:
+        print(operation, ":\t\t", timer[operation])
+    return final

@@ -5,7 +5,7 @@
  * points replace the regions the reference brackets with its own stopwatches
  * ("io" tail, "points in mask", "medoid"), batched over many frames:
  *
- *   cm3d_masks_*            src/nuscenes/2d_to_3d.py:425-428 (RLE decode), :526-527,
+ *   cm3d_masks_*            src/nuscenes/2d_to_3d.py:425-428 (pycocotools RLE decode), :526-527,
  *                           :543-544 (3x3 erosion, bool (W,H) view)
  *   cm3d_aggregate_sweeps   src/nuscenes/2d_to_3d.py:437-465 (close-point removal,
  *                           rotate/translate per sweep, hstack);
@@ -17,6 +17,7 @@
  *   cm3d_compact_segments   src/nuscenes/2d_to_3d.py:617-620 (track_points, gather)
  *   cm3d_medoid             src/nuscenes/2d_to_3d.py:116-119,641-663 (cdist medoid, centroid)
  *   cm3d_pca_obb            src/kitti/2d_to_3d.py:855-876,1524 (open3d OBB -> yaw; parity unpinned)
+ *   cm3d_nearest_lane       src/nuscenes/2d_to_3d.py:277-302 (closest lane point per centroid)
  *
  * Conventions: every pointer is a DEVICE pointer; the caller (PyTorch) owns and
  * sizes every buffer; nothing is allocated, nothing throws; all launches are
@@ -97,6 +98,13 @@ const char *cm3d_error_string(int code);
  * src_off[i] = byte offset of instance i in `masks`. */
 int cm3d_masks_pack_dense(const uint8_t *masks, const int64_t *src_off, const int32_t *inst_desc,
                           int n_inst, int max_words, uint32_t *bits, void *stream);
+
+/* pycocotools compressed `counts` strings -> run lengths, on the device.  counts = the strings of
+ * all instances back to back, byte_off[n_inst+1] their byte offsets.  Instance i's runs are
+ * written to runs[byte_off[i] ..) and zero-padded to byte_off[i+1] (runs has as many uint32 as
+ * counts has bytes), so byte_off doubles as the run_off of cm3d_masks_fill_rle. */
+int cm3d_masks_decode_counts(const uint8_t *counts, const int64_t *byte_off, int n_inst,
+                             uint32_t *runs, void *stream);
 
 /* COCO run lengths (alternating 0-run,1-run; row-major over the (H,W) image) -> bit planes.
  * `bits` must be zero on entry.  run_start is scratch of the same length as runs. */
@@ -191,6 +199,15 @@ int cm3d_medoid_items(int m, int min_pts);
  * conventions in csrc/obb.cu. */
 int cm3d_pca_obb(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
                  int min_pts, float *obb, const int32_t *errflags, void *stream);
+
+/* ---- pass 2: closest lane point --------------------------------------------------------------- */
+
+/* For every centroid (n x 2 doubles) the nearest of m lane points (m x 2 doubles, 16-byte aligned):
+ * idx_out[c] = argmin_k sqrt(dx*dx + dy*dy) in binary64 (first minimum, like numpy.argmin over
+ * scipy's cdist row; -1 when m == 0), dist_out[c] = that distance.  Replaces
+ * lane_yaws_distances_and_coords' cdist + argmin + min (src/nuscenes/2d_to_3d.py:277-302). */
+int cm3d_nearest_lane(const double *centroids_xy, int n, const double *lane_xy, int m,
+                      int32_t *idx_out, double *dist_out, void *stream);
 
 /* Self-test: counts (adds to *mismatches) the floats in [2^-101, FLT_MAX] U {0} on which the
  * medoid kernel's branch-free square root differs from IEEE sqrt.rn.f32.  Must stay 0. */

@@ -71,6 +71,37 @@ def test_dense_and_rle_masks_agree(lifter):
     assert np.array_equal(a.medoid_local, b.medoid_local)
 
 
+def test_counts_strings_decoded_on_device(lifter):
+    """Masks given as pycocotools `counts` strings (the {f}_masks.pkl format) are decoded by
+    cm3d_masks_decode_counts; results equal the run-length path on all three datasets."""
+    from cm3d_b200 import synthetic as S
+    from cm3d_b200.rle import rle_counts_to_runs
+    import torch, ctypes
+    from cm3d_b200 import _native as N
+    for cfg, scale in (("c1", 0.5), ("c4", 0.25)):
+        f = S.make_frame(cfg, 1, scale=scale, dense_masks=False)
+        a = lifter.lift_frames([f])[0]
+        runs = [rle_counts_to_runs(m.counts) for m in f.masks]
+        f.masks = S.compress_rles(f.masks)
+        assert all(isinstance(m.counts, bytes) for m in f.masks)
+        b = lifter.lift_frames([f])[0]
+        assert lifter.last.db.pb.masks_kind == "rle_str"
+        assert np.array_equal(a.seg_offsets, b.seg_offsets)
+        assert np.array_equal(a.seg_point_idx, b.seg_point_idx)
+        assert np.array_equal(a.medoid_point_idx, b.medoid_point_idx)
+        # the decoded runs themselves
+        pb = lifter.last.db.pb
+        d_runs = torch.zeros(pb.mask.size, dtype=torch.int32, device="cuda:0")
+        N.call("cm3d_masks_decode_counts", ctypes.c_void_p(lifter.last.db.mask.data_ptr()),
+               ctypes.c_void_p(lifter.last.db.mask_off.data_ptr()), pb.n_inst, ctypes.c_void_p(d_runs.data_ptr()),
+               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        got = d_runs.cpu().numpy().view(np.uint32)
+        for i, r in enumerate(runs):
+            o0, o1 = int(pb.mask_off[i]), int(pb.mask_off[i + 1])
+            assert np.array_equal(got[o0:o0 + len(r)], r), (cfg, i)
+            assert not got[o0 + len(r):o1].any()
+
+
 @pytest.mark.parametrize("cfg,scale,mask_div", [("c1", 1.0, 1), ("c2", 0.25, 1), ("c3", 0.5, 1), ("c4", 0.25, 1)])
 def test_against_c_oracle(lifter, cfg, scale, mask_div):
     from cm3d_b200 import synthetic as S
@@ -196,3 +227,21 @@ def test_kitti_obb_yaw_against_numpy_oracle(lifter):
             assert np.allclose(r.obb[i, 4:7], wlh, atol=1e-3)
             checked += 1
     assert checked >= 10
+
+
+def test_nearest_lane_bit_exact_vs_scipy(lifter):
+    """cm3d_nearest_lane == argmin/min of scipy's binary64 cdist (nuscenes:277-302), ties included."""
+    from cm3d_b200 import boxes as B
+    from oracle import ref_boxes as RB
+    rng = np.random.default_rng(11)
+    for n, m in ((1, 1), (7, 3), (300, 5000), (64, 100001)):
+        cents = (rng.uniform(-200, 200, (n, 3)) + np.array([1500.0, 900.0, 0.0])).astype(np.float32)
+        lanes = np.concatenate([rng.uniform(-250, 250, (m, 2)) + np.array([1500.0, 900.0]), rng.uniform(-3.2, 3.2, (m, 1))], 1)
+        if m > 10:
+            lanes[m // 2] = lanes[3]                      # duplicate lane point: the first index must win
+            cents[0, :2] = lanes[3, :2]
+        yaws, dist, coords = B.lane_yaws_distances_and_coords(cents, lanes)
+        ry, rd, rc, ri = RB.lane_yaws_distances_and_coords(cents, lanes)
+        assert np.array_equal(dist.view(np.uint64), rd.view(np.uint64))
+        assert np.array_equal(yaws.view(np.uint32), ry.view(np.uint32))
+        assert np.array_equal(coords.view(np.uint32), rc.view(np.uint32))
