@@ -258,11 +258,12 @@ def run_ours(args, rank, world, local_rank):
         if "medoid" in timing:
             kern["medoid"]["pair_distances"] = pairs
             kern["medoid"]["gpairs_per_s"] = pairs / (timing["medoid"] * 1e-3) / 1e9
-            # issue-bound ceiling: 13.8 issue cycles per warp and (row, column) pair step
+            # FMA-pipe ceiling: 10 FP32-pipe lane-ops per pair distance (5 for the cdist chain,
+            # 4 for the correctly rounded sqrt, 1 to accumulate), 128 FP32 lanes per SM and clock
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             mhz = clocks.get("sm_mhz") or 1965.0
-            ceil_gp = n_sm * 4 * 32 * mhz * 1e6 / 13.8 / 1e9
-            kern["medoid"]["bound"] = "fp32 issue slots (O(sum M^2) pair distances; reads only sum M points, L2-resident)"
+            ceil_gp = n_sm * 128 * mhz * 1e6 / 10.0 / 1e9
+            kern["medoid"]["bound"] = "fp32 FMA pipe (O(sum M^2) pair distances; reads only sum M points, L2-resident)"
             kern["medoid"]["peak_gpairs_per_s"] = ceil_gp
             kern["medoid"]["frac"] = kern["medoid"]["gpairs_per_s"] / ceil_gp
         line = {

@@ -26,7 +26,7 @@ MAX_INST = 254
 MAX_VCAMS = 16
 MEDOID_COLS = 256
 CELL = 32
-SW_WORDS, FR_WORDS, VC_WORDS, IN_WORDS, ERR_WORDS = 8, 12, 20, 8, 4
+SW_WORDS, FR_WORDS, VC_WORDS, IN_WORDS, ERR_WORDS = 8, 16, 44, 8, 4
 
 
 def _split64(v: int):
@@ -37,6 +37,68 @@ def _split64(v: int):
 
 def _f32_bits(x) -> int:
     return int(np.float32(x).view(np.int32))
+
+
+def _compose(ops):
+    """fp64 composition of a transform chain: p_out = M p + c; also sum of |translations|_1 after
+    the first op and whether every linear part is orthogonal to 1e-3."""
+    M, c, tau, ok = np.eye(3), np.zeros(3), 0.0, True
+    for k, (kind, m) in enumerate(ops):
+        m = np.asarray(m, np.float64)
+        if kind == "T":
+            c = c + m
+            if k:
+                tau += np.abs(m).sum()
+        else:
+            L = m if kind == "R" else m[:, :3]
+            ok &= bool(np.abs(L @ L.T - np.eye(3)).max() < 1e-3)
+            M, c = L @ M, L @ c
+            if kind == "A":
+                c = c + m[:, 3]
+                tau += np.abs(m[:, 3]).sum()
+    return M, c, tau, ok
+
+
+def cull_planes(cam, W: int, H: int, min_dist32, tref):
+    """Conservative frustum planes of one vcam in q = p + tref coordinates (include/cm3d_b200.h,
+    CM3D_VC_PLANES).  Error budget (u = 2^-24, S = |q|_1, tau = |translations|_1): the reference's
+    fp32 chain is within 96u(S+tau) of the exact composition per coordinate, its pixel numerators
+    within 4u of theirs, and evaluating a plane scaled to |n|_1 <= 1 in fp32 costs <= 6uS + 4u|d|;
+    all of it is below S*2^-17 + mg0, and mg0 is folded into d.  Returns (planes[5,4] f32, flags)."""
+    off = np.tile(np.array([0.0, 0.0, 0.0, 1.0], np.float32), (5, 1))
+    K = np.asarray(cam.K, np.float64)
+    simple = bool(K[0, 1] == 0 and K[1, 0] == 0 and K[0, 0] != 0 and K[1, 1] != 0 and
+                  K[2, 0] == 0 and K[2, 1] == 0 and K[2, 2] == 1)
+    flags = 1 if simple else 0
+    M, c, tau, ok = _compose(cam.ops)
+    if not ok or not (K[2, 0] == 0 and K[2, 1] == 0 and K[2, 2] == 1) or not np.all(np.isfinite(M)):
+        return off, flags
+    tref = np.asarray(tref, np.float64)
+    first_T = len(cam.ops) and cam.ops[0][0] == "T"
+    tau += np.abs(tref + np.asarray(cam.ops[0][1], np.float64)).sum() if first_T else np.abs(tref).sum()
+    c2 = c - M @ tref                                   # p = q - tref
+    cam_planes = [((0.0, 0.0, 1.0), -float(min_dist32)),                     # z > min_dist
+                  (tuple(K[0]), 0.0), ((-K[0, 0], -K[0, 1], W - K[0, 2]), 0.0),   # 0 < r0, r0 < W z
+                  (tuple(K[1]), 0.0), ((-K[1, 0], -K[1, 1], H - K[1, 2]), 0.0)]   # 0 < r1, r1 < H z
+    out = np.zeros((5, 4), np.float64)
+    for k, (abc, d0) in enumerate(cam_planes):
+        abc = np.asarray(abc, np.float64)
+        kappa = 1.75 * np.abs(abc).sum()
+        n = abc @ M / kappa
+        d = (abc @ c2 + d0) / kappa
+        if not (np.abs(n).sum() <= 1.0) or not np.isfinite(d):
+            return off, flags
+        out[k, :3], out[k, 3] = n, d
+    mg0 = 2.0 ** -17 * tau + 2.0 ** -20 * np.abs(out[:, 3]).max() + 1e-30
+    out[:, 3] += mg0
+    out32 = out.astype(np.float32)
+    out32[:, 3] = np.nextafter(out32[:, 3], np.float32(np.inf))   # rounding of d never tightens a plane
+    return out32, flags
+
+
+def _chain_sig(ops) -> int:
+    kinds = {"T": 1, "R": 2, "A": 3}
+    return sum(kinds[k] << (2 * i) for i, (k, _) in enumerate(ops))
 
 
 def _alloc(n, dtype, pin):
@@ -162,9 +224,15 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
         members = [[] for _ in keys]
         for i in range(I):
             members[key_index[(int(f.cam_nums[i]),) + sizes[i]]].append(i)
+        first = f.cams[keys[0][0]].ops if keys else []
+        tref = np.asarray(first[0][1], np.float32) if (first and first[0][0] == "T") else np.zeros(3, np.float32)
+        sigs = {_chain_sig(f.cams[k[0]].ops) for k in keys}
         for k, mem in zip(keys, members):
             cam = f.cams[k[0]]
             row = np.zeros(VC_WORDS, np.int32)
+            planes, flags = cull_planes(cam, k[1], k[2], f.min_dist_f32(), tref)
+            row[20:40] = planes.reshape(-1).view(np.int32)
+            row[40] = flags
             row[0] = len(chains)
             chains.append(encode_chain(cam.ops))
             row[1:13] = cam.viewpad34().reshape(-1).view(np.int32)
@@ -181,7 +249,9 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
         min_pts = 4 if f.dataset == "kitti" else 1          # kitti/2d_to_3d.py:1479-1480 skips M <= 3
         frame_desc[fi] = [t_begin, ti, v_begin, len(keys), ii, I,
                           _f32_bits(f.close_thresh if use_close else 0.0), int(use_close),
-                          _f32_bits(f.min_dist_f32()), cnt_total, min_pts, ii]
+                          _f32_bits(f.min_dist_f32()), cnt_total, min_pts, ii,
+                          _f32_bits(tref[0]), _f32_bits(tref[1]), _f32_bits(tref[2]),
+                          sigs.pop() if len(sigs) == 1 else -1]
         cnt_total += ntf * I
         for i in range(I):
             W, H = sizes[i]

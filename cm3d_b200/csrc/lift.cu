@@ -113,6 +113,8 @@ struct VcamS {
     int list_begin, list_count;
     const uint32_t *grid;          // instance lookup grid of this vcam
     int grid_nx, grid_nwords;
+    float4 plane[5];               // conservative cull planes in q = p + tref coordinates (cm3d_b200.h)
+    int flags, pad0, pad1, pad2;   // bit 0: simple viewpad
 };
 struct InstS {
     int xmin, ymin, xmax, ymax;   // eroded bbox, clamped to >= 1 (the reference drops fx==0 / fy==0)
@@ -126,6 +128,8 @@ struct FrameTables {
     uint8_t list[CM3D_MAX_INST + 2];
     int n_vcams, n_inst;
     float min_depth;
+    float tref[3];
+    int chain_sig;
 };
 
 __device__ __forceinline__ void load_frame_tables(FrameTables &ft, const int32_t *__restrict__ fd,
@@ -143,6 +147,16 @@ __device__ __forceinline__ void load_frame_tables(FrameTables &ft, const int32_t
         ft.n_vcams = nv;
         ft.n_inst = ni;
         ft.min_depth = __int_as_float(fd[CM3D_FR_MIN_DEPTH_BITS]);
+        ft.tref[0] = __int_as_float(fd[CM3D_FR_TREF]);
+        ft.tref[1] = __int_as_float(fd[CM3D_FR_TREF + 1]);
+        ft.tref[2] = __int_as_float(fd[CM3D_FR_TREF + 2]);
+        ft.chain_sig = fd[CM3D_FR_CHAIN_SIG];
+    }
+    for (int k = threadIdx.x; k < nv * 21; k += blockDim.x) {
+        const int v = k / 21, wd = k - v * 21;
+        const int32_t *vd = vcam_desc + (size_t)(v0 + v) * CM3D_VC_WORDS;
+        if (wd < 20) reinterpret_cast<float *>(ft.vcam[v].plane)[wd] = __int_as_float(vd[CM3D_VC_PLANES + wd]);
+        else ft.vcam[v].flags = vd[CM3D_VC_FLAGS];
     }
     for (int k = threadIdx.x; k < nv * CM3D_CHAIN_WORDS; k += blockDim.x) {
         const int v = k / CM3D_CHAIN_WORDS, wd = k - v * CM3D_CHAIN_WORDS;
@@ -299,6 +313,99 @@ k_build_vcam_grid(const int32_t *__restrict__ vcam_desc, const int32_t *__restri
     }
 }
 
+// Chain signatures (sum kind_k * 4^k) the kernels are specialised for; anything else runs the
+// generic path that reads the op kinds from shared memory.
+constexpr int kSigTRTR = 1 + (2 << 2) + (1 << 4) + (2 << 6);   // nuScenes: global -> ego -> camera
+constexpr int kSigTR = 1 + (2 << 2);                           // Waymo: vehicle -> camera
+constexpr int kSigAAR = 3 + (3 << 2) + (2 << 4);               // KITTI: ref -> velo -> ref -> rect
+constexpr int kSigGeneric = -1;
+
+template <int SIG>
+__device__ __forceinline__ int op_kind(const VcamS &vc, int k)
+{
+    return SIG == kSigGeneric ? vc.kind[k] : ((SIG >> (2 * k)) & 3);
+}
+
+// Exact projection of NP points into vcam `vc` (same arithmetic as project_n), with the op kinds
+// fixed at compile time and the zero terms of a plain pinhole viewpad dropped: with
+// K = [[fx,0,cx],[0,fy,cy],[0,0,1]] the reference's 4-term chains reduce to fma(cx,z,fx*x),
+// fma(cy,z,fy*y) and z for every finite point (adding a 0*y or 0*1 term changes at most the sign
+// of a zero), and non-finite points are rejected either way.
+template <int SIG, int NP>
+__device__ __forceinline__ void project_sig(const VcamS &vc, float min_depth, const float (&px)[NP],
+                                            const float (&py)[NP], const float (&pz)[NP], int32_t (&code)[NP])
+{
+    float x[NP], y[NP], z[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { x[p] = px[p]; y[p] = py[p]; z[p] = pz[p]; }
+#pragma unroll
+    for (int k = 0; k < CM3D_MAX_CHAIN; ++k) {
+        const int kind = op_kind<SIG>(vc, k);
+        if (kind == CM3D_OP_END) break;
+        const float4 a = vc.m[k][0], b = vc.m[k][1], c = vc.m[k][2];
+        if (kind == CM3D_OP_T) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                x[p] = __fadd_rn(x[p], a.x); y[p] = __fadd_rn(y[p], a.y); z[p] = __fadd_rn(z[p], a.z);
+            }
+        } else if (kind == CM3D_OP_R) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float u = x[p], v = y[p], w = z[p];
+                x[p] = __fmaf_rn(a.z, w, __fmaf_rn(a.y, v, __fmul_rn(a.x, u)));
+                y[p] = __fmaf_rn(b.y, w, __fmaf_rn(b.x, v, __fmul_rn(a.w, u)));
+                z[p] = __fmaf_rn(c.x, w, __fmaf_rn(b.w, v, __fmul_rn(b.z, u)));
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float u = x[p], v = y[p], w = z[p];
+                x[p] = __fmaf_rn(1.0f, a.w, __fmaf_rn(w, a.z, __fmaf_rn(v, a.y, __fmul_rn(u, a.x))));
+                y[p] = __fmaf_rn(1.0f, b.w, __fmaf_rn(w, b.z, __fmaf_rn(v, b.y, __fmul_rn(u, b.x))));
+                z[p] = __fmaf_rn(1.0f, c.w, __fmaf_rn(w, c.z, __fmaf_rn(v, c.y, __fmul_rn(u, c.x))));
+            }
+        }
+    }
+    const float4 k0 = vc.vp[0], k1 = vc.vp[1], k2 = vc.vp[2];
+    const bool simple = (vc.flags & 1) != 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        code[p] = -1;
+        if (!(z[p] > min_depth)) continue;
+        float r0, r1, r2;
+        if (simple) {
+            r0 = __fmaf_rn(k0.z, z[p], __fmul_rn(k0.x, x[p]));
+            r1 = __fmaf_rn(k1.z, z[p], __fmul_rn(k1.y, y[p]));
+            r2 = z[p];
+        } else {
+            r0 = __fmaf_rn(k0.w, 1.0f, __fmaf_rn(k0.z, z[p], __fmaf_rn(k0.y, y[p], __fmul_rn(k0.x, x[p]))));
+            r1 = __fmaf_rn(k1.w, 1.0f, __fmaf_rn(k1.z, z[p], __fmaf_rn(k1.y, y[p], __fmul_rn(k1.x, x[p]))));
+            r2 = __fmaf_rn(k2.w, 1.0f, __fmaf_rn(k2.z, z[p], __fmaf_rn(k2.y, y[p], __fmul_rn(k2.x, x[p]))));
+        }
+        if (r2 > 0.0f && (!(r0 > 0.0f) || !(r1 > 0.0f) || r0 >= __fmul_rn(r2, vc.wcap) || r1 >= __fmul_rn(r2, vc.hcap)))
+            continue;
+        const float u = __fdiv_rn(r0, r2), v = __fdiv_rn(r1, r2);
+        if (u > 0.0f && u < vc.wlim && v > 0.0f && v < vc.hlim)
+            code[p] = (int32_t)floorf(u) | ((int32_t)floorf(v) << 16);
+    }
+}
+
+// Up to four ids (1..254) appended in any order, one per byte, zeros on top -> ascending from byte 0
+// with the zeros still on top (the layout k_compact reads).  An overflowed word (byte 3 == 255)
+// is recomputed by k_compact and passes through.
+__device__ __forceinline__ uint32_t hit_sort(uint32_t h)
+{
+    if (h < 0x100u || (h >> 24) == 0xffu) return h;          // zero or one id, or overflow
+    uint32_t b0 = h & 0xffu, b1 = (h >> 8) & 0xffu, b2 = (h >> 16) & 0xffu, b3 = h >> 24;
+    // empty bytes sort last: map 0 -> 256
+    b0 = b0 ? b0 : 256u; b1 = b1 ? b1 : 256u; b2 = b2 ? b2 : 256u; b3 = b3 ? b3 : 256u;
+    uint32_t t;
+#define CM3D_CSWAP(a, b) t = min(a, b); b = max(a, b); a = t;
+    CM3D_CSWAP(b0, b1) CM3D_CSWAP(b2, b3) CM3D_CSWAP(b0, b2) CM3D_CSWAP(b1, b3) CM3D_CSWAP(b1, b2)
+#undef CM3D_CSWAP
+    return (b0 & 0xffu) | ((b1 & 0xffu) << 8) | ((b2 & 0xffu) << 16) | ((b3 & 0xffu) << 24);
+}
+
 // Sorted insert of id (1..254) into a 4-byte hit word; byte 3 becomes 255 on overflow.
 __device__ __forceinline__ uint32_t hit_insert(uint32_t hw, uint32_t id)
 {
@@ -317,8 +424,106 @@ __device__ __forceinline__ uint32_t hit_insert(uint32_t hw, uint32_t id)
     return out;
 }
 
-// K2 (count pass): one block per tile of the aggregated cloud.
-__global__ void __launch_bounds__(kBlock)
+// K2 (count pass): one block per tile of the aggregated cloud, 4 consecutive slots per thread.
+// Per vcam: (1) every point is tested against the vcam's five conservative cull planes (3 FMAs +
+// a compare each, early exit; points are in firing order, so whole warps drop out together);
+// (2) warps with a survivor run the exact chain; in-image points append (pixel, slot) to a
+// per-vcam list in shared memory; (3) the list is walked by ALL threads of the block (instance
+// lookup grid -> bbox -> one bit probe), so the walk is load balanced instead of divergent.
+// Hit words are kept in shared memory during the walk (a slot is touched by one thread per vcam
+// pass) and leave with one 16-byte store per thread.
+template <int SIG>
+__device__ __forceinline__ void project_count_tile(FrameTables &ft, int *s_hist, uint32_t *s_hw, int32_t *s_lcode,
+                                                   uint16_t *s_lslot, int *s_ln, const float *__restrict__ xyzw,
+                                                   int64_t n_slots, int64_t base, int cnt, int32_t *__restrict__ pix)
+{
+    const int s0 = threadIdx.x * 4;
+    const int np = max(0, min(4, cnt - s0));
+    float xs[4] = {0.f, 0.f, 0.f, 0.f}, ys[4] = {0.f, 0.f, 0.f, 0.f}, zs[4] = {0.f, 0.f, 0.f, 0.f};
+    float qx[4], qy[4], qz[4], nmg[4];
+    if (np > 0) {
+        const float4 X = __ldg(reinterpret_cast<const float4 *>(xyzw + base + s0));
+        const float4 Y = __ldg(reinterpret_cast<const float4 *>(xyzw + n_slots + base + s0));
+        const float4 Z = __ldg(reinterpret_cast<const float4 *>(xyzw + 2 * n_slots + base + s0));
+        xs[0] = X.x; xs[1] = X.y; xs[2] = X.z; xs[3] = X.w;
+        ys[0] = Y.x; ys[1] = Y.y; ys[2] = Y.z; ys[3] = Y.w;
+        zs[0] = Z.x; zs[1] = Z.y; zs[2] = Z.z; zs[3] = Z.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        qx[k] = __fadd_rn(xs[k], ft.tref[0]); qy[k] = __fadd_rn(ys[k], ft.tref[1]); qz[k] = __fadd_rn(zs[k], ft.tref[2]);
+        nmg[k] = -((fabsf(qx[k]) + fabsf(qy[k])) + fabsf(qz[k])) * 0x1p-17f;     // -S * 2^-17
+    }
+    *reinterpret_cast<uint4 *>(s_hw + s0) = make_uint4(0u, 0u, 0u, 0u);
+
+    for (int v = 0; v < ft.n_vcams; ++v) {
+        const VcamS &vc = ft.vcam[v];
+        // (1) cull planes: plane-outer so each plane is one LDS.128 for the thread's four points;
+        // a thread leaves as soon as none of its points is left (depth first, then left/right, ...)
+        unsigned cand = (1u << np) - 1u;
+#pragma unroll
+        for (int pl = 0; pl < 5; ++pl) {
+            if (cand == 0) break;
+            const float4 n = vc.plane[pl];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float val = __fmaf_rn(n.x, qx[k], __fmaf_rn(n.y, qy[k], __fmaf_rn(n.z, qz[k], n.w)));
+                if (val < nmg[k]) cand &= ~(1u << k);
+            }
+        }
+        int32_t code[4] = {-1, -1, -1, -1};
+        // (2) exact chain for warps that still hold a candidate
+        if (cand != 0) {
+            project_sig<SIG, 4>(vc, ft.min_depth, xs, ys, zs, code);
+            int n_in = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!((cand >> k) & 1u)) code[k] = -1;       // k >= np, or culled (then it is -1 anyway)
+                n_in += code[k] >= 0;
+            }
+            if (n_in) {
+                int at = atomicAdd(s_ln + v, n_in);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (code[k] >= 0) { s_lcode[at] = code[k]; s_lslot[at] = (uint16_t)(s0 + k); ++at; }
+            }
+        }
+        if (pix) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < np) pix[(int64_t)v * n_slots + base + s0 + k] = code[k];
+        }
+        __syncthreads();
+        // (3) walk the in-image list of this vcam
+        const int n_list = s_ln[v];
+        for (int e = threadIdx.x; e < n_list; e += blockDim.x) {
+            const int32_t code = s_lcode[e];
+            const int fx = code & 0xffff, fy = code >> 16;
+            if (fx == 0 || fy == 0) continue;                 // `logical_and(floored_points, ...)` quirk
+            const uint32_t *cell = vc.grid + (size_t)((fy / CM3D_CELL) * vc.grid_nx + fx / CM3D_CELL) * vc.grid_nwords;
+            const uint32_t bit = 1u << (fx & 31);
+            uint32_t h = 0;
+            bool touched = false;
+            for (int w = 0; w < vc.grid_nwords; ++w) {
+                uint32_t c = __ldg(cell + w);
+                while (c) {
+                    const int j = ft.list[vc.list_begin + w * 32 + (__ffs(c) - 1)];
+                    c &= c - 1u;
+                    const InstS &si = ft.inst[j];
+                    if (__ldg(si.plane + (size_t)fy * si.pitch + (fx >> 5)) & bit) {
+                        if (!touched) { h = s_hw[s_lslot[e]]; touched = true; }
+                        h = (h >> 24) ? (h | 0xff000000u) : ((h << 8) | (uint32_t)(j + 1));   // append, newest in byte 0
+                        atomicAdd(&s_hist[j], 1);
+                    }
+                }
+            }
+            if (touched) s_hw[s_lslot[e]] = h;
+        }
+        __syncthreads();                       // the list buffers are reused by the next vcam
+    }
+}
+
+__global__ void __launch_bounds__(kBlock, 4)
 k_project_count(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *__restrict__ tile_cnt,
                 const int32_t *__restrict__ tile_sweep, const int32_t *__restrict__ sweep_desc,
                 const int32_t *__restrict__ frame_desc, const int32_t *__restrict__ vcam_desc,
@@ -329,44 +534,34 @@ k_project_count(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *
 {
     __shared__ FrameTables ft;
     __shared__ int s_hist[CM3D_MAX_INST + 2];
+    __shared__ __align__(16) uint32_t s_hw[kTile];
+    __shared__ int32_t s_lcode[kTile];
+    __shared__ uint16_t s_lslot[kTile];
+    __shared__ int s_ln[CM3D_MAX_VCAMS];     // in-image list length, one counter per vcam pass
 
     const int t = blockIdx.x;
     const int f = sweep_desc[(size_t)tile_sweep[t] * CM3D_SW_WORDS + CM3D_SW_FRAME];
     const int32_t *fd = frame_desc + (size_t)f * CM3D_FR_WORDS;
     load_frame_tables(ft, fd, vcam_desc, cam_inst_list, inst_desc, inst_bbox, chains, bits, vcam_grid);
     for (int j = threadIdx.x; j < CM3D_MAX_INST + 2; j += blockDim.x) s_hist[j] = 0;
+    if (threadIdx.x < CM3D_MAX_VCAMS) s_ln[threadIdx.x] = 0;
     __syncthreads();
 
     const int cnt = tile_cnt[t];
     const int64_t base = (int64_t)t * kTile;
-    const int s0 = threadIdx.x * 4;
-    if (s0 < cnt) {
-        const float4 X = __ldg(reinterpret_cast<const float4 *>(xyzw + base + s0));
-        const float4 Y = __ldg(reinterpret_cast<const float4 *>(xyzw + n_slots + base + s0));
-        const float4 Z = __ldg(reinterpret_cast<const float4 *>(xyzw + 2 * n_slots + base + s0));
-        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-        uint32_t hw[4] = {0u, 0u, 0u, 0u};
-        const int np = min(4, cnt - s0);
-        for (int v = 0; v < ft.n_vcams; ++v) {
-            const VcamS &vc = ft.vcam[v];
-            int32_t code[4];
-            project_n<4>(vc, ft.min_depth, xs, ys, zs, code);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k >= np) continue;
-                if (pix) pix[(int64_t)v * n_slots + base + s0 + k] = code[k];
-                if (code[k] < 0) continue;
-                uint32_t h = hw[k];
-                hits_in_vcam(ft, vc, code[k], [&](int j) {
-                    h = hit_insert(h, (uint32_t)j + 1u);
-                    atomicAdd(&s_hist[j], 1);
-                });
-                hw[k] = h;
-            }
-        }
-        *reinterpret_cast<uint4 *>(hits + base + s0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    switch (ft.chain_sig) {
+    case kSigTRTR: project_count_tile<kSigTRTR>(ft, s_hist, s_hw, s_lcode, s_lslot, s_ln, xyzw, n_slots, base, cnt, pix); break;
+    case kSigTR:   project_count_tile<kSigTR>(ft, s_hist, s_hw, s_lcode, s_lslot, s_ln, xyzw, n_slots, base, cnt, pix); break;
+    case kSigAAR:  project_count_tile<kSigAAR>(ft, s_hist, s_hw, s_lcode, s_lslot, s_ln, xyzw, n_slots, base, cnt, pix); break;
+    default:       project_count_tile<kSigGeneric>(ft, s_hist, s_hw, s_lcode, s_lslot, s_ln, xyzw, n_slots, base, cnt, pix); break;
     }
     __syncthreads();
+    const int s0 = threadIdx.x * 4;
+    if (s0 < cnt) {
+        uint4 hw = *reinterpret_cast<const uint4 *>(s_hw + s0);
+        hw.x = hit_sort(hw.x); hw.y = hit_sort(hw.y); hw.z = hit_sort(hw.z); hw.w = hit_sort(hw.w);
+        *reinterpret_cast<uint4 *>(hits + base + s0) = hw;
+    }
     const int tl = t - fd[CM3D_FR_TILE_BEGIN], ntf = fd[CM3D_FR_TILE_END] - fd[CM3D_FR_TILE_BEGIN];
     uint16_t *out = tile_inst_cnt + (size_t)fd[CM3D_FR_CNT_OFF] + tl;
     for (int j = threadIdx.x; j < ft.n_inst; j += blockDim.x) out[(size_t)j * ntf] = (uint16_t)s_hist[j];

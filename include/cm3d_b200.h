@@ -74,12 +74,22 @@ enum { CM3D_SW_RAW_LO = 0, CM3D_SW_RAW_HI, CM3D_SW_NPTS, CM3D_SW_STRIDE, CM3D_SW
 enum { CM3D_FR_TILE_BEGIN = 0, CM3D_FR_TILE_END, CM3D_FR_VCAM_BEGIN, CM3D_FR_NVCAMS,
        CM3D_FR_INST_BEGIN, CM3D_FR_NINST, CM3D_FR_CLOSE_BITS, CM3D_FR_USE_CLOSE,
        CM3D_FR_MIN_DEPTH_BITS, CM3D_FR_CNT_OFF, CM3D_FR_MIN_MEDOID_PTS, CM3D_FR_LIST_BEGIN,
-       CM3D_FR_WORDS };
+       CM3D_FR_TREF = 12 /* 3 floats: q = p + tref is the point the cull planes are evaluated on */,
+       CM3D_FR_CHAIN_SIG = 15 /* sum kind_k * 4^k when all vcams of the frame share it, else -1 */,
+       CM3D_FR_WORDS = 16 };
 /* vcam_desc[v][CM3D_VC_WORDS]: one per (camera, mask size) of a frame */
 enum { CM3D_VC_CHAIN = 0, CM3D_VC_VIEWPAD = 1 /* 12 floats */, CM3D_VC_W = 13, CM3D_VC_H,
        CM3D_VC_LIST_BEGIN /* into cam_inst_list, relative to the frame's LIST_BEGIN */,
        CM3D_VC_LIST_COUNT, CM3D_VC_FRAME, CM3D_VC_GRID_OFF /* word offset into vcam_grid */,
-       CM3D_VC_GRID_NX /* cells per row, ceil(W/CM3D_CELL) */, CM3D_VC_WORDS = 20 };
+       CM3D_VC_GRID_NX /* cells per row, ceil(W/CM3D_CELL) */,
+       CM3D_VC_PLANES = 20 /* 5 x (nx,ny,nz,d) floats: conservative frustum planes, see below */,
+       CM3D_VC_FLAGS = 40 /* bit 0: viewpad is [[fx,0,cx,0],[0,fy,cy,0],[0,0,1,0]] */,
+       CM3D_VC_WORDS = 44 };
+/* Cull planes (host-built in fp64 by cm3d_b200/batch.py, optional: (0,0,0,1) x 5 disables them).
+ * For q = fl(p + tref) and S = |qx|+|qy|+|qz|, a point whose plane value n.q + d is below
+ * -S * 2^-17 for ANY of the five planes (depth, left, right, top, bottom) provably fails the
+ * reference's depth / image-bounds test in that vcam, whatever the rounding of the exact chain;
+ * only the survivors run the exact fp32 chain.  The planes never change a result. */
 #define CM3D_CELL 32            /* pixels per side of a vcam_grid cell */
 /* inst_desc[i][CM3D_IN_WORDS] */
 enum { CM3D_IN_BITS_LO = 0, CM3D_IN_BITS_HI, CM3D_IN_W, CM3D_IN_H, CM3D_IN_PITCH, CM3D_IN_VCAM,

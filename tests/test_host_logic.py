@@ -161,3 +161,35 @@ def test_sharded_lift_two_ranks_gloo(tmp_path):
     for p in procs:
         assert p.wait(timeout=240) == 0
     assert out.read_text() == "ok 6"
+
+
+def test_cull_planes_never_drop_an_in_image_point():
+    """The host-built frustum planes (cm3d_b200.batch.cull_planes, CM3D_VC_PLANES) are conservative:
+    every point the oracle finds inside a camera image keeps a plane value above -S*2^-17 with half
+    the margin to spare (fp64 evaluation of the fp32 coefficients), on all three datasets - and the
+    planes do cull most (point, camera) pairs."""
+    from cm3d_b200 import synthetic as S
+    from cm3d_b200.batch import cull_planes
+    from oracle import c_oracle as CO
+    culled = pairs = 0
+    for cfg, scale in (("c1", 0.5), ("c2", 0.1), ("c3", 0.25), ("c4", 0.2)):
+        f = S.make_frame(cfg, 2, scale=scale, mask_div=2)
+        aggr = CO.aggregate(f)                                   # (rows, N) reference cloud
+        xyz = np.ascontiguousarray(aggr[:3], np.float32)
+        first = f.cams[0].ops
+        tref = np.asarray(first[0][1], np.float32) if first and first[0][0] == "T" else np.zeros(3, np.float32)
+        q = (xyz + tref[:, None]).astype(np.float32).astype(np.float64)
+        Sq = np.abs(q).sum(0)
+        for c, cam in enumerate(f.cams):
+            sizes = {f.mask_size(i) for i in range(f.n_instances) if f.cam_nums[i] == c}
+            for (W, H) in sizes:
+                planes, flags = cull_planes(cam, W, H, f.min_dist_f32(), tref)
+                assert flags == 1 and not np.array_equal(planes[0], [0, 0, 0, 1])
+                val = planes[:, :3].astype(np.float64) @ q + planes[:, 3:4].astype(np.float64)   # (5, N)
+                pix = CO.project(xyz, cam, W, H, f.min_dist)
+                inside = pix >= 0
+                assert inside.any()
+                assert (val[:, inside] > -0.5 * Sq[inside] * 2.0 ** -17).all(), (cfg, c)
+                culled += int((val < -Sq * 2.0 ** -17).any(0).sum())
+                pairs += xyz.shape[1]
+    assert culled > 0.6 * pairs
