@@ -26,7 +26,7 @@ MAX_INST = 254
 MAX_VCAMS = 16
 MEDOID_COLS = 256
 CELL = 32
-SW_WORDS, FR_WORDS, VC_WORDS, IN_WORDS, ERR_WORDS = 8, 16, 44, 8, 4
+SW_WORDS, FR_WORDS, VC_WORDS, IN_WORDS, ERR_WORDS = 8, 20, 44, 8, 4
 
 
 def _split64(v: int):
@@ -138,6 +138,7 @@ class PackedBatch:
     grid_words: int = 0             # words of the per-vcam instance lookup grids
     max_cells: int = 0
     any_kitti: bool = False         # a KITTI frame is in the batch -> Lifter also computes the OBB yaw
+    frame_datasets: List[str] = field(default_factory=list)
 
     def table(self, name: str, words: int = 1) -> np.ndarray:
         o, n = self.off[name], self.off[name + "_n"]
@@ -251,7 +252,9 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
                           _f32_bits(f.close_thresh if use_close else 0.0), int(use_close),
                           _f32_bits(f.min_dist_f32()), cnt_total, min_pts, ii,
                           _f32_bits(tref[0]), _f32_bits(tref[1]), _f32_bits(tref[2]),
-                          sigs.pop() if len(sigs) == 1 else -1]
+                          sigs.pop() if len(sigs) == 1 else -1,
+                          _f32_bits(0.0 if f.floor_thresh is None else f.floor_thresh), int(f.floor_thresh is not None),
+                          0, 0]
         cnt_total += ntf * I
         for i in range(I):
             W, H = sizes[i]
@@ -318,5 +321,6 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
                      raw, meta, mask, mo[:mask_off_arr.size], off, frame_inst, frame_vcam_cams,
                      {"raw": raw_t, "meta": meta_t, "mask": mask_t, "mask_off": mo_t})
     pb.any_kitti = any(f.dataset == "kitti" for f in frames)
+    pb.frame_datasets = [f.dataset for f in frames]
     pb.grid_words, pb.max_cells = grid_words, max_cells
     return pb

@@ -59,6 +59,8 @@ k_aggregate(const float *__restrict__ raw, const int32_t *__restrict__ tile_swee
     mbar_wait(&s_bar, 0);
 
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const bool use_floor = fd[CM3D_FR_USE_FLOOR] != 0;          // default-off ground threshold
+    const float floor_thr = __int_as_float(fd[CM3D_FR_FLOOR_BITS]);
     float px[kPerThread], py[kPerThread], pz[kPerThread], pw[kPerThread];
     unsigned ball[kPerThread];
 #pragma unroll
@@ -71,6 +73,10 @@ k_aggregate(const float *__restrict__ raw, const int32_t *__restrict__ tile_swee
             x = q[0]; y = q[1]; z = q[2];
             if (fourth == 1) w = q[3];
             if (use_close && fabsf(x) < close_thr && fabsf(y) < close_thr) keep = false;
+            apply_chain(s_chain, x, y, z);
+            // `aggr_pc_points[2] > floor_thresh` of the reference's commented-out ground filter
+            // (src/kitti/2d_to_3d.py:1186-1190), on the aggregated (transformed) cloud
+            if (use_floor && !(z > floor_thr)) keep = false;
         }
         px[r] = x; py[r] = y; pz[r] = z; pw[r] = w;
         ball[r] = __ballot_sync(0xffffffffu, keep);
@@ -94,9 +100,7 @@ k_aggregate(const float *__restrict__ raw, const int32_t *__restrict__ tile_swee
     for (int r = 0; r < kPerThread; ++r) {
         if (ball[r] & (1u << lane)) {
             const int64_t slot = (int64_t)t * kTile + s_gcnt[r * (kBlock / 32) + warp] + __popc(ball[r] & lanemask_lt());
-            float x = px[r], y = py[r], z = pz[r];
-            apply_chain(s_chain, x, y, z);
-            ox[slot] = x; oy[slot] = y; oz[slot] = z;
+            ox[slot] = px[r]; oy[slot] = py[r]; oz[slot] = pz[r];
             if (fourth) ow[slot] = pw[r];
         }
     }
@@ -908,6 +912,19 @@ extern "C" int cm3d_scan_segments(const int32_t *tile_cnt, const uint16_t *tile_
     CM3D_LAUNCH_CHECK();
     k_scan_batch<<<1, 1024, 0, (cudaStream_t)stream>>>(seg_count, inst_desc, frame_desc, n_inst_total, seg_cap,
                                                        seg_off, item_off, item_inst, medoid_best, errflags);
+    CM3D_LAUNCH_CHECK();
+    return CM3D_OK;
+}
+
+extern "C" int cm3d_schedule_segments(const int32_t *frame_desc, const int32_t *inst_desc, int n_inst_total,
+                                      int64_t seg_cap, int32_t *seg_off, int32_t *item_off, int32_t *item_inst,
+                                      unsigned long long *medoid_best, int32_t *errflags, void *stream)
+{
+    if (n_inst_total < 0 || seg_cap < 0) return CM3D_EINVAL;
+    if (!frame_desc || !seg_off || !item_off || !item_inst || !medoid_best || !errflags || (n_inst_total && !inst_desc))
+        return CM3D_EINVAL;
+    k_scan_batch<<<1, 1024, 0, (cudaStream_t)stream>>>(seg_off + 1, inst_desc, frame_desc, n_inst_total, seg_cap, seg_off,
+                                                       item_off, item_inst, medoid_best, errflags);
     CM3D_LAUNCH_CHECK();
     return CM3D_OK;
 }

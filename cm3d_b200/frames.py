@@ -109,6 +109,7 @@ class FrameSpec:
     min_dist: float = 2.3                      # depth threshold (python float in the ref)
     token: str = ""
     meta: dict = field(default_factory=dict)
+    floor_thresh: Optional[float] = None       # default-off extension: keep aggregated points with z > floor_thresh
 
     def __post_init__(self):
         self.sweeps = [np.ascontiguousarray(s, dtype=np.float32) for s in self.sweeps]
@@ -161,6 +162,8 @@ class LiftResult:
     pix: Optional[np.ndarray] = None           # (C,N) int32 packed fx|fy<<16 or -1, debug only
     yaw: Optional[np.ndarray] = None           # (I,) fp32 KITTI OBB yaw, nan if n/a
     obb: Optional[np.ndarray] = None           # (I,16) yaw, centre xyz, wlh, R' row-major (KITTI)
+    box: Optional[np.ndarray] = None           # (I,8) orientation search: centre, extents (along, across, up), heading, area
+    raw_counts: Optional[np.ndarray] = None    # (I,) member counts before the neighbour-count filter (when it ran)
 
     @property
     def counts(self) -> np.ndarray:

@@ -54,6 +54,8 @@ class DeviceOutputs:
     bits: Optional[torch.Tensor] = None
     bbox: Optional[torch.Tensor] = None
     obb: Optional[torch.Tensor] = None     # (I,16): yaw, centre, wlh, R' (KITTI frames / want_obb)
+    box: Optional[torch.Tensor] = None     # (I,8): orientation search (box_search=n_angles)
+    seg_off_raw: Optional[torch.Tensor] = None   # (I+1,) offsets before the neighbour-count filter
 
 
 class Lifter:
@@ -68,6 +70,8 @@ class Lifter:
         self._streams = None        # (copy, compute) streams of the pipelined path, created once: torch's
         #                             caching allocator pools memory per stream, so fresh streams per call
         #                             would cudaMalloc the whole workspace again (~100 ms)
+        self.denoise = None         # default-off extensions, see run()
+        self.box_search = None
         self.launches = 0           # kernels launched by this object (bench.py reports it)
         self.timing = None          # dict label -> [(start_event, end_event)] when bench.py profiles
 
@@ -108,7 +112,14 @@ class Lifter:
         return lay
 
     def run(self, db: DeviceBatch, seg_cap: Optional[int] = None, want_pix: bool = False,
-            want_col_sums: bool = False, do_medoid: bool = True, want_obb: Optional[bool] = None) -> DeviceOutputs:
+            want_col_sums: bool = False, do_medoid: bool = True, want_obb: Optional[bool] = None,
+            denoise=None, box_search: Optional[int] = None) -> DeviceOutputs:
+        """One launch sequence over a packed batch.  Default-off extensions (not executed by the
+        reference, parity unpinned): `denoise=(radius, min_neighbors)` drops member points with fewer
+        than min_neighbors members of their instance within radius before the medoid / boxes;
+        `box_search=n_angles` adds the orientation / extent search (LiftResult.box)."""
+        denoise = denoise if denoise is not None else self.denoise
+        box_search = box_search if box_search is not None else self.box_search
         pb, dev = db.pb, self.device
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         F, I, T = pb.n_frames, pb.n_inst, pb.n_tiles
@@ -191,6 +202,27 @@ class Lifter:
                seg_cap, pb.max_inst_per_frame, _ptr(o("errflags")), st)
         self.launches += 1 if T else 0
 
+        # ---- default-off: neighbour-count outlier filter -> filtered segments
+        seg_off_raw = None
+        if denoise is not None and I:
+            radius, min_nb = float(denoise[0]), int(denoise[1])
+            keep = torch.empty(seg_cap, dtype=torch.uint8, device=dev)
+            item_first = torch.empty(I + 1, **i32)
+            seg_off2 = torch.zeros(I + 2, **i32)
+            kept = ctypes.c_void_p(seg_off2.data_ptr() + 4)          # counts staged at seg_off2[1..]
+            self._call("denoise", "cm3d_neighbor_filter", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I,
+                       seg_cap // MEDOID_COLS + I, radius, min_nb, _ptr(item_first), _ptr(keep), kept, st)
+            self._call("denoise", "cm3d_schedule_segments", _ptr(db.tab("frame_desc")), _ptr(inst_desc), I, seg_cap,
+                       _ptr(seg_off2), _ptr(o("item_off")), _ptr(item_inst), _ptr(medoid_best), _ptr(o("errflags")), st)
+            seg_point_idx2 = torch.empty(seg_cap, **i32)
+            seg_xyzw2 = torch.empty(4 * seg_cap, dtype=torch.float32, device=dev)
+            self._call("denoise", "cm3d_filter_segments", _ptr(seg_xyzw), _ptr(seg_point_idx), seg_cap, _ptr(o("seg_off")),
+                       _ptr(keep), _ptr(seg_off2), I, _ptr(seg_xyzw2), _ptr(seg_point_idx2), _ptr(o("errflags")), st)
+            self.launches += 4
+            seg_off_raw = o("seg_off")[:I + 1].clone()
+            o("seg_off")[:I + 1].copy_(seg_off2[:I + 1])
+            seg_point_idx, seg_xyzw = seg_point_idx2, seg_xyzw2
+
         # ---- medoid
         col_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if want_col_sums else None
         if do_medoid and I:
@@ -208,8 +240,18 @@ class Lifter:
             self._call("pca_obb", "cm3d_pca_obb", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, 4, _ptr(obb),
                        _ptr(o("errflags")), st)
             self.launches += 1
+        box = None
+        if box_search and I:
+            kitti_flags = {f == "kitti" for f in pb.frame_datasets}
+            if len(kitti_flags) > 1:
+                raise ValueError("box_search: a batch must not mix KITTI (y up) with nuScenes/Waymo (z up) frames")
+            up_axis = 1 if pb.any_kitti else 2
+            box = torch.empty(I * 8, dtype=torch.float32, device=dev)
+            self._call("box_search", "cm3d_box_search", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, up_axis,
+                       int(box_search), 1, _ptr(box), _ptr(o("errflags")), st)
+            self.launches += 1
         return DeviceOutputs(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, xyzw, tile_cnt, tile_prefix,
-                             pix, col_sums, hits, bits, bbox, obb)
+                             pix, col_sums, hits, bits, bbox, obb, box, seg_off_raw)
 
     # ------------------------------------------------------------------ device -> host
     def fetch_labels(self, do: DeviceOutputs, pinned: Optional[torch.Tensor] = None) -> dict:
@@ -329,6 +371,8 @@ class Lifter:
         pix_all = do.pix.view(16, -1).cpu().numpy() if (with_pix and do.pix is not None) else None
         fdesc = pb.table("frame_desc", FR_WORDS)
         obb_all = do.obb.view(-1, 16).cpu().numpy() if do.obb is not None else None
+        box_all = do.box.view(-1, 8).cpu().numpy() if do.box is not None else None
+        raw_off = do.seg_off_raw.cpu().numpy().astype(np.int64) if do.seg_off_raw is not None else None
         out = []
         for f in range(pb.n_frames):
             i0, i1 = int(pb.frame_inst[f]), int(pb.frame_inst[f + 1])
@@ -343,6 +387,10 @@ class Lifter:
             if obb_all is not None:
                 r.yaw = obb_all[i0:i1, 0].copy()
                 r.obb = obb_all[i0:i1].copy()
+            if box_all is not None:
+                r.box = box_all[i0:i1].copy()
+            if raw_off is not None:
+                r.raw_counts = np.diff(raw_off[i0:i1 + 1]).astype(np.int32)
             if with_points:
                 tb, te = int(fdesc[f, 0]), int(fdesc[f, 1])
                 keep = (np.arange(TILE)[None, :] < tile_cnt[tb:te, None]).reshape(-1)
@@ -353,16 +401,17 @@ class Lifter:
         return out
 
     def lift_frames(self, frames: Sequence[FrameSpec], with_points: bool = True, with_pix: bool = False,
-                    want_col_sums: bool = False) -> List[LiftResult]:
+                    want_col_sums: bool = False, denoise=None, box_search: Optional[int] = None) -> List[LiftResult]:
         """Synchronous convenience: pack, upload, run, read back; retries once with exact
         segment capacity if the default guess was too small."""
         pb = self.pack(frames)
         db = self.upload(pb)
-        do = self.run(db, want_pix=with_pix, want_col_sums=want_col_sums)
+        kw = dict(want_pix=with_pix, want_col_sums=want_col_sums, denoise=denoise, box_search=box_search)
+        do = self.run(db, **kw)
         labels = self.fetch_labels(do)
         need = self.check_flags(labels)
         if need:
-            do = self.run(db, seg_cap=need, want_pix=with_pix, want_col_sums=want_col_sums)
+            do = self.run(db, seg_cap=need, **kw)
             labels = self.fetch_labels(do)
             if self.check_flags(labels):
                 raise N.Cm3dError("segment capacity retry failed")

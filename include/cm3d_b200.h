@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 4
+#define CM3D_ABI_VERSION 5
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
@@ -76,7 +76,8 @@ enum { CM3D_FR_TILE_BEGIN = 0, CM3D_FR_TILE_END, CM3D_FR_VCAM_BEGIN, CM3D_FR_NVC
        CM3D_FR_MIN_DEPTH_BITS, CM3D_FR_CNT_OFF, CM3D_FR_MIN_MEDOID_PTS, CM3D_FR_LIST_BEGIN,
        CM3D_FR_TREF = 12 /* 3 floats: q = p + tref is the point the cull planes are evaluated on */,
        CM3D_FR_CHAIN_SIG = 15 /* sum kind_k * 4^k when all vcams of the frame share it, else -1 */,
-       CM3D_FR_WORDS = 16 };
+       CM3D_FR_FLOOR_BITS = 16, CM3D_FR_USE_FLOOR = 17 /* default-off ground threshold: keep z > floor */,
+       CM3D_FR_WORDS = 20 };
 /* vcam_desc[v][CM3D_VC_WORDS]: one per (camera, mask size) of a frame */
 enum { CM3D_VC_CHAIN = 0, CM3D_VC_VIEWPAD = 1 /* 12 floats */, CM3D_VC_W = 13, CM3D_VC_H,
        CM3D_VC_LIST_BEGIN /* into cam_inst_list, relative to the frame's LIST_BEGIN */,
@@ -209,6 +210,38 @@ int cm3d_medoid_items(int m, int min_pts);
  * conventions in csrc/obb.cu. */
 int cm3d_pca_obb(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
                  int min_pts, float *obb, const int32_t *errflags, void *stream);
+
+/* ---- default-off extensions (north star (3)/(4); never executed by the reference: PARITY UNPINNED) ---- */
+
+/* Per-instance outlier filter by neighbour counting: keep[p] = 1 when at least min_neighbors members
+ * of the same instance (the point itself included) lie within `radius` of member p
+ * (d2 = (dx*dx + dy*dy) + dz*dz in fp32 <= fl(radius*radius)).  kept_count[i] = survivors of
+ * instance i; item_first[n_inst_total+1] is scratch; max_items >= sum ceil(M_i/256)
+ * (seg_cap/256 + n_inst_total always is).  Stands where the reference has its dead
+ * `clusters_hdbscan` (src/kitti/2d_to_3d.py:159-174). */
+int cm3d_neighbor_filter(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
+                         int max_items, float radius, int min_neighbors, int32_t *item_first,
+                         uint8_t *keep, int32_t *kept_count, void *stream);
+
+/* Segment offsets + medoid schedule from per-instance counts staged in seg_off[1..n_inst_total]
+ * (pass kept_count = seg_off + 1 above): the batch-level half of cm3d_scan_segments. */
+int cm3d_schedule_segments(const int32_t *frame_desc, const int32_t *inst_desc, int n_inst_total,
+                           int64_t seg_cap, int32_t *seg_off, int32_t *item_off, int32_t *item_inst,
+                           unsigned long long *medoid_best, int32_t *errflags, void *stream);
+
+/* Ordered compaction of the kept points of every instance into new segments (offsets seg_off2). */
+int cm3d_filter_segments(const float *seg_xyzw, const int32_t *seg_point_idx, int64_t seg_cap,
+                         const int32_t *seg_off, const uint8_t *keep, const int32_t *seg_off2,
+                         int n_inst_total, float *seg_xyzw2, int32_t *seg_point_idx2,
+                         const int32_t *errflags, void *stream);
+
+/* Block-level orientation / extent search: box[8*i..] = centre xyz, extent along the heading, across
+ * it, up, heading in [0, pi/2) about `up_axis` (0/1/2), footprint area - the heading among
+ * k*pi/(2*n_angles), k < n_angles, with the smallest axis-aligned footprint of the rotated points
+ * (first minimum); NaN for instances with fewer than min_pts points. */
+int cm3d_box_search(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
+                    int up_axis, int n_angles, int min_pts, float *box, const int32_t *errflags,
+                    void *stream);
 
 /* ---- pass 2: closest lane point --------------------------------------------------------------- */
 

@@ -63,7 +63,7 @@ def lane_yaws_distances_and_coords(all_centroids, all_lane_pts):
     DistMat = scipy.spatial.distance.cdist(all_centroids[:, :2], all_lane_pts[:, :2])
     min_lane_indices = np.argmin(DistMat, axis=1)
     distances = np.min(DistMat, axis=1)
-    all_lane_pts = np.array(all_lane_pts)
+    all_lane_pts = all_lane_pts.numpy()
     min_lanes = all_lane_pts[min_lane_indices]
     return min_lanes[:, 2], distances, min_lanes[:, :2], min_lane_indices
 

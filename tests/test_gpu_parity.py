@@ -245,3 +245,55 @@ def test_nearest_lane_bit_exact_vs_scipy(lifter):
         assert np.array_equal(dist.view(np.uint64), rd.view(np.uint64))
         assert np.array_equal(yaws.view(np.uint32), ry.view(np.uint32))
         assert np.array_equal(coords.view(np.uint32), rc.view(np.uint32))
+
+
+def test_default_off_extensions_against_numpy_oracle(lifter):
+    """Ground threshold, neighbour-count outlier filter and orientation/extent search (north star
+    (3)/(4); PARITY UNPINNED vs the reference, which never executes them).  Keep flags, filtered
+    point lists and the medoid of the filtered set: bit-exact vs oracle/extras_oracle.py + the C
+    oracle; box centre/extent 1e-3 m, heading 1e-3 rad (or an equal-area tie)."""
+    from cm3d_b200 import synthetic as S
+    from oracle import c_oracle as CO
+    from oracle import extras_oracle as EO
+    frames = [S.make_frame("c1", 5, scale=0.5), S.make_frame("c4", 5, scale=0.25)]
+    frames[0].floor_thresh = 0.25
+    plain = lifter.lift_frames([S.make_frame("c1", 5, scale=0.5)], with_points=True)[0]
+    res = lifter.lift_frames(frames, with_points=True, denoise=(0.6, 6), box_search=90)
+    assert res[0].n_points < plain.n_points                       # the ground threshold removed points
+    checked = 0
+    for f, r in zip(frames, res):
+        o = CO.lift_frame_c(f, record_pix=False, do_medoid=False)
+        aggr = o["aggr"]
+        if f.floor_thresh is not None:
+            kept_cols = np.flatnonzero(aggr[2] > np.float32(f.floor_thresh))
+            assert r.n_points == kept_cols.size
+            assert np.array_equal(r.aggr_points[:3].view(np.uint32), aggr[:3, kept_cols].view(np.uint32))
+            remap = -np.ones(aggr.shape[1], np.int64)
+            remap[kept_cols] = np.arange(kept_cols.size)
+        for i in range(f.n_instances):
+            idx = np.asarray(o["idx"][i], np.int64)
+            if f.floor_thresh is not None:
+                idx = remap[idx]
+                idx = idx[idx >= 0]
+            assert r.raw_counts[i] == idx.size
+            pts = r.aggr_points[:3][:, idx]
+            keep = EO.neighbor_keep(pts, 0.6, 6) if idx.size else np.zeros(0, bool)
+            assert np.array_equal(r.instance_points(i), idx[keep]), (f.dataset, i)
+            if keep.sum() == 0:
+                assert r.medoid_local[i] == -1 and np.isnan(r.box[i]).all()
+                continue
+            kp = pts[:, keep]
+            assert r.medoid_local[i] == CO.medoid(kp)
+            c, ext, th, area = EO.box_search(kp, 2, 90)
+            assert np.allclose(r.box[i, 3:6], ext, atol=1e-3) or abs(r.box[i, 7] - area) <= 1e-5 * max(area, 1e-6)
+            if abs(r.box[i, 6] - th) < 1e-3:
+                assert np.allclose(r.box[i, :3], c, atol=1e-3)
+            else:
+                assert abs(r.box[i, 7] - area) <= 1e-5 * max(area, 1e-6)     # equal-area tie between headings
+            # every kept point lies inside the box (1 mm)
+            cs, sn = np.cos(r.box[i, 6]), np.sin(r.box[i, 6])
+            du, dv = kp[0] - r.box[i, 0], kp[1] - r.box[i, 1]
+            u, v = du * cs + dv * sn, dv * cs - du * sn
+            assert np.abs(u).max() <= r.box[i, 3] / 2 + 1e-3 and np.abs(v).max() <= r.box[i, 4] / 2 + 1e-3
+            checked += 1
+    assert checked >= 20
