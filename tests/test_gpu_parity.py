@@ -297,3 +297,45 @@ def test_default_off_extensions_against_numpy_oracle(lifter):
             assert np.abs(u).max() <= r.box[i, 3] / 2 + 1e-3 and np.abs(v).max() <= r.box[i, 4] / 2 + 1e-3
             checked += 1
     assert checked >= 20
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c3", "c4"])
+def test_full_size_configs(lifter, cfg):
+    """BASELINE.json's full sizes (C2: 10 sweeps x 34.7k pts x 6 cams x 50 inst; C3: KITTI 120k pts;
+    C4: Waymo 180k pts x 5 cams x 80 inst): cloud and per-instance point sets bit-exact against the C
+    oracle; medoids through size-independent properties - the reported medoid is the first minimum of
+    the GPU's own column sums, and those sums are bit-identical to the C oracle's on a sample of
+    instances (the full O(sum M^2) oracle would take minutes)."""
+    from cm3d_b200 import synthetic as S
+    from oracle import c_oracle as CO
+    f = S.make_frame(cfg, 11)
+    r = lifter.lift_frames([f], with_points=True, want_col_sums=True)[0]
+    sums = lifter.last.col_sums.cpu().numpy()
+    o = CO.lift_frame_c(f, record_pix=False, do_medoid=False)
+    assert r.n_points == o["n_points"]
+    aggr = o["aggr"].T if f.dataset == "kitti" else o["aggr"]          # KITTI keeps the reference's (N,3) rows
+    assert np.array_equal(r.aggr_points[:aggr.shape[0]].view(np.uint32), np.ascontiguousarray(aggr).view(np.uint32))
+    sizes = []
+    for i in range(f.n_instances):
+        idx = r.instance_points(i)
+        assert np.array_equal(idx, o["idx"][i]), (cfg, i)
+        assert np.all(np.diff(idx) > 0)                      # ascending = the reference's boolean-index order
+        sizes.append(idx.size)
+        min_pts = 4 if f.dataset == "kitti" else 1
+        if idx.size < min_pts:
+            assert r.medoid_local[i] == -1
+            continue
+        s = sums[r.seg_offsets[i]:r.seg_offsets[i + 1]]
+        assert r.medoid_local[i] == int(np.argmin(s))        # first minimum, like torch.argmin
+        assert r.medoid_point_idx[i] == idx[r.medoid_local[i]]
+        assert np.array_equal(r.centroids[i].view(np.uint32), r.aggr_points[:3, idx[r.medoid_local[i]]].view(np.uint32))
+    order = np.argsort(sizes)
+    sample = [int(k) for k in order if sizes[k] > 0][:4] + [int(order[len(order) // 2]), int(order[-3])]
+    for i in sample:
+        idx = r.instance_points(i)
+        if idx.size == 0:
+            continue
+        j, ref = CO.medoid(r.aggr_points[:3][:, idx], want_sums=True)
+        got = sums[r.seg_offsets[i]:r.seg_offsets[i + 1]]
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (cfg, i, idx.size)
+        assert r.medoid_local[i] == j or f.dataset == "kitti" and idx.size < 4
