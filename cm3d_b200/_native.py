@@ -10,8 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libcm3d_b200.so")
-ABI_VERSION = 5
+LIB_PATH = os.environ.get("CM3D_B200_LIB") or os.path.join(_HERE, "_lib", "libcm3d_b200.so")   # env: kernel experiments
+ABI_VERSION = 6
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -21,8 +21,8 @@ _L = ctypes.c_int64
 PROTOTYPES = {
     "cm3d_masks_pack_dense": [_P, _P, _P, _I, _I, _P, _P],
     "cm3d_masks_decode_counts": [_P, _P, _I, _P, _P],
-    "cm3d_masks_fill_rle": [_P, _P, _P, _P, _I, _I, _P, _P, _P],
-    "cm3d_masks_erode3x3": [_P, _P, _I, _I, _P, _P, _P],
+    "cm3d_masks_fill_rle": [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "cm3d_masks_erode3x3": [_P, _P, _P, _I, _I, _P, _P, _P],
     "cm3d_aggregate_sweeps": [_P, _P, _I, _P, _P, _P, _P, _P, _P],
     "cm3d_build_vcam_grid": [_P, _I, _I, _P, _P, _P, _P, _P],
     "cm3d_project_membership": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],

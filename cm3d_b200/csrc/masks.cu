@@ -126,10 +126,12 @@ k_rle_decode(const uint8_t *__restrict__ bytes, const int64_t *__restrict__ byte
 __global__ void __launch_bounds__(256)
 k_rle_prefix(const uint32_t *__restrict__ runs, const int64_t *__restrict__ run_off,
              const int32_t *__restrict__ inst_desc, uint32_t *__restrict__ run_start,
-             int32_t *__restrict__ errflags)
+             int32_t *__restrict__ row_range, int32_t *__restrict__ errflags)
 {
     __shared__ uint32_t s_w[8];
     __shared__ uint32_t s_carry;
+    __shared__ unsigned s_lo, s_hi;           // first / one-past-last set pixel (flat index) of the mask
+    if (threadIdx.x == 0) { s_lo = 0xffffffffu; s_hi = 0u; }
     const int i = blockIdx.x;
     const int64_t r0 = run_off[i], r1 = run_off[i + 1];
     const int32_t *d = inst_desc + i * CM3D_IN_WORDS;
@@ -151,11 +153,21 @@ k_rle_prefix(const uint32_t *__restrict__ runs, const int64_t *__restrict__ run_
         uint32_t woff = s_carry;
         for (unsigned w = 0; w < warp; ++w) woff += s_w[w];
         if (r < r1) run_start[r] = woff + inc - v;
+        if (r < r1 && v != 0u && ((r - r0) & 1)) {       // a non-empty 1-run
+            atomicMin(&s_lo, woff + inc - v);
+            atomicMax(&s_hi, min(woff + inc, total));
+        }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) s_carry = woff + inc;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && s_carry != total) atomicExch(&errflags[CM3D_ERR_RLE_SIZE], i + 1);
+    if (threadIdx.x == 0) {
+        if (s_carry != total) atomicExch(&errflags[CM3D_ERR_RLE_SIZE], i + 1);
+        const uint32_t W = (uint32_t)d[CM3D_IN_W];
+        // rows that hold a set pixel: erosion only needs to look at those (everything else stays 0)
+        row_range[2 * i] = s_hi ? (int32_t)(s_lo / W) : 0x7fffffff;
+        row_range[2 * i + 1] = s_hi ? (int32_t)((s_hi - 1) / W) : -1;
+    }
 }
 
 // One warp per 1-run: OR its pixels into the (zeroed) bit plane, row by row.
@@ -219,18 +231,25 @@ __device__ __forceinline__ uint32_t hmin3(const uint32_t *__restrict__ row, int 
 
 __global__ void __launch_bounds__(256)
 k_erode3x3(const uint32_t *__restrict__ bits_in, const int32_t *__restrict__ inst_desc,
-           uint32_t *__restrict__ bits_out, int32_t *__restrict__ bbox)
+           const int32_t *__restrict__ row_range, uint32_t *__restrict__ bits_out, int32_t *__restrict__ bbox)
 {
     const int i = blockIdx.y;
     const int32_t *d = inst_desc + i * CM3D_IN_WORDS;
     const int W = d[CM3D_IN_W], H = d[CM3D_IN_H], pitch = d[CM3D_IN_PITCH];
     const int wd = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = wd < H * pitch;
+    bool live = wd < H * pitch;
     uint32_t out = 0;
     int y = 0, xw = 0;
     if (live) {
         y = wd / pitch;
         xw = wd - y * pitch;
+        const int64_t off = join64(d[CM3D_IN_BITS_LO], d[CM3D_IN_BITS_HI]);
+        if (row_range && (y < row_range[2 * i] || y > row_range[2 * i + 1])) {
+            bits_out[off + wd] = 0u;            // no set pixel in this row: nothing survives, nothing to read
+            live = false;
+        }
+    }
+    if (live) {
         const int64_t off = join64(d[CM3D_IN_BITS_LO], d[CM3D_IN_BITS_HI]);
         const uint32_t *plane = bits_in + off;
         const uint32_t tailmask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xffffffffu;
@@ -292,15 +311,15 @@ extern "C" int cm3d_masks_decode_counts(const uint8_t *counts, const int64_t *by
 
 extern "C" int cm3d_masks_fill_rle(const uint32_t *runs, const int64_t *run_off, uint32_t *run_start,
                                    const int32_t *inst_desc, int n_inst, int max_runs, uint32_t *bits,
-                                   int32_t *errflags, void *stream)
+                                   int32_t *row_range, int32_t *errflags, void *stream)
 {
     if (n_inst < 0 || max_runs < 0) return CM3D_EINVAL;
     if (n_inst == 0) return CM3D_OK;
-    if (!run_off || !inst_desc || !bits || !errflags) return CM3D_EINVAL;
-    if (max_runs == 0) return CM3D_OK;
+    if (!run_off || !inst_desc || !bits || !row_range || !errflags) return CM3D_EINVAL;
     if (!runs || !run_start) return CM3D_EINVAL;
-    k_rle_prefix<<<n_inst, 256, 0, (cudaStream_t)stream>>>(runs, run_off, inst_desc, run_start, errflags);
+    k_rle_prefix<<<n_inst, 256, 0, (cudaStream_t)stream>>>(runs, run_off, inst_desc, run_start, row_range, errflags);
     CM3D_LAUNCH_CHECK();
+    if (max_runs == 0) return CM3D_OK;
     const int one_runs = (max_runs + 1) / 2;          // 1-runs sit at odd positions
     dim3 grid((one_runs + 7) / 8, n_inst);
     k_rle_fill<<<grid, 256, 0, (cudaStream_t)stream>>>(runs, run_off, run_start, inst_desc, bits);
@@ -308,8 +327,8 @@ extern "C" int cm3d_masks_fill_rle(const uint32_t *runs, const int64_t *run_off,
     return CM3D_OK;
 }
 
-extern "C" int cm3d_masks_erode3x3(const uint32_t *bits_in, const int32_t *inst_desc, int n_inst,
-                                   int max_words, uint32_t *bits_out, int32_t *bbox, void *stream)
+extern "C" int cm3d_masks_erode3x3(const uint32_t *bits_in, const int32_t *inst_desc, const int32_t *row_range,
+                                   int n_inst, int max_words, uint32_t *bits_out, int32_t *bbox, void *stream)
 {
     if (n_inst < 0 || max_words < 0) return CM3D_EINVAL;
     if (n_inst == 0) return CM3D_OK;
@@ -318,7 +337,7 @@ extern "C" int cm3d_masks_erode3x3(const uint32_t *bits_in, const int32_t *inst_
     CM3D_LAUNCH_CHECK();
     if (max_words == 0) return CM3D_OK;
     dim3 grid((max_words + 255) / 256, n_inst);
-    k_erode3x3<<<grid, 256, 0, (cudaStream_t)stream>>>(bits_in, inst_desc, bits_out, bbox);
+    k_erode3x3<<<grid, 256, 0, (cudaStream_t)stream>>>(bits_in, inst_desc, row_range, bits_out, bbox);
     CM3D_LAUNCH_CHECK();
     return CM3D_OK;
 }

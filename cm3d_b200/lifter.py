@@ -140,6 +140,7 @@ class Lifter:
         bits = torch.empty(max(pb.bits_words, 1), **i32)
         bbox = torch.empty(max(I, 1) * 4, **i32)
         inst_desc = db.tab("inst_desc")
+        row_range = None
         if I:
             if pb.masks_kind == "dense":
                 self._call("masks_pack", "cm3d_masks_pack_dense", _ptr(db.mask), _ptr(db.mask_off), _ptr(inst_desc), I,
@@ -153,11 +154,12 @@ class Lifter:
                     self._call("masks_decode", "cm3d_masks_decode_counts", _ptr(db.mask), _ptr(db.mask_off), I, _ptr(runs), st)
                     self.launches += 1
                 run_start = torch.empty(max(runs.numel(), 1), **i32)
+                row_range = torch.empty(2 * I, **i32)
                 self._call("masks_rle", "cm3d_masks_fill_rle", _ptr(runs), _ptr(db.mask_off), _ptr(run_start), _ptr(inst_desc),
-                       I, pb.max_runs, _ptr(bits_raw), _ptr(o("errflags")), st)
+                       I, pb.max_runs, _ptr(bits_raw), _ptr(row_range), _ptr(o("errflags")), st)
                 self.launches += 3
-            self._call("masks_erode", "cm3d_masks_erode3x3", _ptr(bits_raw), _ptr(inst_desc), I, pb.max_words, _ptr(bits),
-                   _ptr(bbox), st)
+            self._call("masks_erode", "cm3d_masks_erode3x3", _ptr(bits_raw), _ptr(inst_desc), _ptr(row_range), I,
+                       pb.max_words, _ptr(bits), _ptr(bbox), st)
             self.launches += 2
 
         vcam_grid = torch.empty(max(pb.grid_words, 1), **i32)

@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 5
+#define CM3D_ABI_VERSION 6
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
@@ -118,15 +118,18 @@ int cm3d_masks_decode_counts(const uint8_t *counts, const int64_t *byte_off, int
                              uint32_t *runs, void *stream);
 
 /* COCO run lengths (alternating 0-run,1-run; row-major over the (H,W) image) -> bit planes.
- * `bits` must be zero on entry.  run_start is scratch of the same length as runs. */
+ * `bits` must be zero on entry.  run_start is scratch of the same length as runs.
+ * row_range[2*i], [2*i+1] = first / last image row of instance i that holds a set pixel
+ * ({INT_MAX,-1} when the mask is empty): lets the erosion skip the empty rows. */
 int cm3d_masks_fill_rle(const uint32_t *runs, const int64_t *run_off, uint32_t *run_start,
                         const int32_t *inst_desc, int n_inst, int max_runs, uint32_t *bits,
-                        int32_t *errflags, void *stream);
+                        int32_t *row_range, int32_t *errflags, void *stream);
 
 /* cv2.erode(mask, ones(3,3)) on bit planes; bbox[i] = {xmin,ymin,xmax,ymax} of the eroded
- * set bits ({INT_MAX,INT_MAX,-1,-1} if none). */
-int cm3d_masks_erode3x3(const uint32_t *bits_in, const int32_t *inst_desc, int n_inst, int max_words,
-                        uint32_t *bits_out, int32_t *bbox, void *stream);
+ * set bits ({INT_MAX,INT_MAX,-1,-1} if none).  row_range (optional, from cm3d_masks_fill_rle; NULL =
+ * look at every row): rows outside it are written as zeros without reading the input. */
+int cm3d_masks_erode3x3(const uint32_t *bits_in, const int32_t *inst_desc, const int32_t *row_range,
+                        int n_inst, int max_words, uint32_t *bits_out, int32_t *bbox, void *stream);
 
 /* Instance lookup grid: for every vcam, cell (cx,cy) of CM3D_CELL^2 pixels holds
  * ceil(list_count/32) words whose bit k says "the eroded bbox of the vcam's k-th instance touches
