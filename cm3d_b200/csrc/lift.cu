@@ -699,6 +699,8 @@ k_scan_batch(const int32_t *__restrict__ seg_count, const int32_t *__restrict__ 
 // ascending instance order per 32-slot group, so every segment is in ascending point order.
 // The ballot walk runs twice: once to count members per (group, instance), once - after an
 // exclusive prefix over the groups - to scatter.
+constexpr int kFastInst = 24;    // k_compact: instances per tile the ballot-per-instance path handles
+
 struct PendingHits {
     uint32_t word;       // up to four ids, ascending, one per byte (non-overflow points)
     uint32_t bm[8];      // membership bitmask of an overflow point (more than four masks)
@@ -754,12 +756,86 @@ k_compact(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *__rest
         any |= hw[r] != 0;
         ovf |= (hw[r] >> 24) == 0xffu;
     }
-    if (threadIdx.x == 0) { s_any = 0; s_ovf = 0; }
+    __shared__ int s_np, s_pbase[kFastInst];
+    __shared__ uint8_t s_plist[kFastInst];
+    __shared__ uint16_t s_pc[kFastInst * kGroups];
+    if (threadIdx.x == 0) { s_any = 0; s_ovf = 0; s_np = 0; }
     __syncthreads();
     if (any) s_any = 1;
     if (ovf) s_ovf = 1;
     __syncthreads();
     if (!s_any) return;
+
+    // ---- fast path: few instances in this tile (points are in firing order, so a tile of 1024
+    // consecutive points usually sees a handful) and no overflow word.  For every present instance:
+    // one ballot per 32-slot group gives its members, an exclusive scan over the 32 groups their
+    // ranks; members leave in slot order, so consecutive lanes write consecutive addresses.
+    {
+        const int tl0 = t - fd[CM3D_FR_TILE_BEGIN], ntf0 = fd[CM3D_FR_TILE_END] - fd[CM3D_FR_TILE_BEGIN];
+        const int i0 = fd[CM3D_FR_INST_BEGIN];
+        for (int j = threadIdx.x; j < ni; j += blockDim.x) {
+            const int32_t *bj = tile_inst_base + (size_t)fd[CM3D_FR_CNT_OFF] + (size_t)j * ntf0;
+            const int b0 = bj[tl0];
+            const int b1 = tl0 + 1 < ntf0 ? bj[tl0 + 1] : seg_off[i0 + j + 1] - seg_off[i0 + j];
+            if (b1 > b0) {
+                const int k = atomicAdd(&s_np, 1);
+                if (k < kFastInst) { s_plist[k] = (uint8_t)j; s_pbase[k] = seg_off[i0 + j] + b0; }
+            }
+        }
+        __syncthreads();
+        const int np = s_np;
+        if (!s_ovf && np <= kFastInst) {
+            float px[kPerThread], py[kPerThread], pz[kPerThread], pw[kPerThread];
+#pragma unroll
+            for (int r = 0; r < kPerThread; ++r) {
+                px[r] = py[r] = pz[r] = pw[r] = 0.f;
+                if (hw[r] != 0) {
+                    const int64_t s = base + r * kBlock + threadIdx.x;
+                    px[r] = xyzw[s]; py[r] = xyzw[n_slots + s]; pz[r] = xyzw[2 * n_slots + s];
+                    if (fourth) pw[r] = xyzw[3 * n_slots + s];
+                }
+            }
+            for (int k = 0; k < np; ++k) {
+                const uint32_t pat = ((uint32_t)s_plist[k] + 1u) * 0x01010101u;
+#pragma unroll
+                for (int r = 0; r < kPerThread; ++r) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, __vcmpeq4(hw[r], pat) != 0u);
+                    if (lane == 0) s_pc[k * kGroups + r * (kBlock / 32) + warp] = (uint16_t)__popc(bal);
+                }
+            }
+            __syncthreads();
+            for (int k = warp; k < np; k += kBlock / 32) {          // lane = group
+                const int c = s_pc[k * kGroups + lane];
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= (unsigned)o) inc += v;
+                }
+                s_pc[k * kGroups + lane] = (uint16_t)(inc - c);
+            }
+            __syncthreads();
+            float *sx = seg_xyzw, *sy = seg_xyzw + seg_cap, *sz = seg_xyzw + 2 * seg_cap, *sw = seg_xyzw + 3 * seg_cap;
+            const int tp0 = tile_prefix[t];
+            for (int k = 0; k < np; ++k) {
+                const uint32_t pat = ((uint32_t)s_plist[k] + 1u) * 0x01010101u;
+                const int kb = s_pbase[k];
+#pragma unroll
+                for (int r = 0; r < kPerThread; ++r) {
+                    const bool mem = __vcmpeq4(hw[r], pat) != 0u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, mem);
+                    if (mem) {
+                        const int64_t dst = (int64_t)kb + s_pc[k * kGroups + r * (kBlock / 32) + warp] + __popc(bal & lanemask_lt());
+                        if (dst < seg_cap) {
+                            seg_point_idx[dst] = tp0 + r * kBlock + threadIdx.x;
+                            sx[dst] = px[r]; sy[dst] = py[r]; sz[dst] = pz[r]; sw[dst] = pw[r];
+                        }
+                    }
+                }
+            }
+            return;
+        }
+    }
 
     uint16_t *s_gc = reinterpret_cast<uint16_t *>(dyn_smem);
     int *s_base = reinterpret_cast<int *>(dyn_smem + ((kGroups * ni * 2 + 15) & ~15));
