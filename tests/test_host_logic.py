@@ -193,3 +193,69 @@ def test_cull_planes_never_drop_an_in_image_point():
                 culled += int((val < -Sq * 2.0 ** -17).any(0).sum())
                 pairs += xyz.shape[1]
     assert culled > 0.6 * pairs
+
+
+def test_cull_planes_random_cameras_and_boundary_points():
+    """Randomised: arbitrary chains (T-R-T-R, T-R, A-A-R, R-T, A), poses up to 3 km from the origin,
+    points pushed onto the frustum faces.  No point the C oracle puts inside the image may be culled
+    (fp64 evaluation of the fp32 planes must stay above -S*2^-17 with half the margin to spare)."""
+    from scipy.spatial.transform import Rotation
+    from cm3d_b200.batch import cull_planes
+    from cm3d_b200.frames import CamSpec, op_A, op_R, op_T
+    from oracle import c_oracle as CO
+    rng = np.random.default_rng(77)
+    n_inside = n_culled = n_pairs = 0
+    for trial in range(60):
+        kind = trial % 5
+        Rw = Rotation.random(random_state=int(rng.integers(1 << 30))).as_matrix()
+        Rc = Rotation.random(random_state=int(rng.integers(1 << 30))).as_matrix()
+        tw = rng.uniform(-3000, 3000, 3) * (1 if kind in (0, 3) else 0.001)
+        tc = rng.uniform(-2, 2, 3)
+        if kind == 0:
+            ops = [op_T(-tw), op_R(Rw.T), op_T(-tc), op_R(Rc.T)]
+        elif kind == 1:
+            ops = [op_T(-tc), op_R(Rc.T)]
+        elif kind == 2:
+            A1 = np.concatenate([Rw, tc[:, None]], 1)
+            A2 = np.concatenate([Rw.T, (-Rw.T @ tc)[:, None]], 1)
+            ops = [op_A(A2), op_A(A1), op_R(Rc)]
+        elif kind == 3:
+            ops = [op_R(Rw), op_T(tw * 0.01)]
+        else:
+            ops = [op_A(np.concatenate([Rc, tc[:, None]], 1))]
+        W, H = int(rng.integers(200, 2000)), int(rng.integers(100, 1300))
+        f = rng.uniform(0.3, 2.5) * W
+        K = np.array([[f, 0, rng.uniform(0.3, 0.7) * W], [0, f * rng.uniform(0.9, 1.1), rng.uniform(0.3, 0.7) * H], [0, 0, 1]])
+        cam = CamSpec(ops, K)
+        # points: random in the camera frame incl. exactly-on-boundary rays, mapped back to the cloud frame in fp64
+        n = 4000
+        z = np.exp(rng.uniform(np.log(0.5), np.log(150.0), n))
+        u = rng.uniform(-0.2 * W, 1.2 * W, n)
+        v = rng.uniform(-0.2 * H, 1.2 * H, n)
+        edge = rng.integers(0, 6, n)
+        u = np.where(edge == 0, rng.uniform(0, 1e-3, n), np.where(edge == 1, W - 1 - rng.uniform(0, 1e-3, n), u))
+        v = np.where(edge == 2, rng.uniform(0, 1e-3, n), np.where(edge == 3, H - 1 - rng.uniform(0, 1e-3, n), v))
+        z = np.where(edge == 4, 2.3 + rng.uniform(0, 1e-4, n), z)
+        pc = np.stack([(u - K[0, 2]) * z / K[0, 0], (v - K[1, 2]) * z / K[1, 1], z])
+        M, c = np.eye(3), np.zeros(3)                       # p_cam = M p + c
+        for kd, m in ops:
+            m = np.asarray(m, np.float64)
+            if kd == "T":
+                c = c + m
+            elif kd == "R":
+                M, c = m @ M, m @ c
+            else:
+                M, c = m[:, :3] @ M, m[:, :3] @ c + m[:, 3]
+        p = np.linalg.solve(M, pc - c[:, None]).astype(np.float32)
+        tref = np.asarray(ops[0][1], np.float32) if ops[0][0] == "T" else np.zeros(3, np.float32)
+        planes, flags = cull_planes(cam, W, H, np.float32(2.3), tref)
+        assert flags == 1
+        q = (p + tref[:, None]).astype(np.float32).astype(np.float64)
+        Sq = np.abs(q).sum(0)
+        val = planes[:, :3].astype(np.float64) @ q + planes[:, 3:4].astype(np.float64)
+        inside = CO.project(p, cam, W, H, 2.3) >= 0
+        n_inside += int(inside.sum())
+        assert (val[:, inside] > -0.5 * Sq[inside] * 2.0 ** -17).all(), (trial, kind)
+        n_culled += int((val < -Sq * 2.0 ** -17).any(0).sum())
+        n_pairs += n
+    assert n_inside > 20000 and n_culled > 0.2 * n_pairs
