@@ -289,8 +289,17 @@ def run_ours(args, rank, world, local_rank):
                 kern[k]["algo_bytes"] = algo[k]
                 kern[k]["gbps"] = algo[k] / (ms * 1e-3) / 1e9
         hbm_k = max((k for k in kern if k in ("aggregate", "project_count", "compact")), key=lambda k: kern[k]["ms"])
+        traffic, traffic_src = None, None
+        try:        # DRAM bytes per launch of that kernel from the committed ncu capture of this same command
+            with open(os.path.join(ROOT, "profiles", "r01c_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("frames_per_launch") == args.batch:
+                traffic, traffic_src = tj["dram_bytes_per_launch"].get("k_" + hbm_k), tj["source"]
+        except Exception:
+            pass
         roof = {"kernel": hbm_k, "bound": "hbm", "achieved": kern[hbm_k]["gbps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[hbm_k]["gbps"] / peak, "traffic": None, "peak_source": peak_src}
+                "frac": kern[hbm_k]["gbps"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algo_bytes": algo[hbm_k], "peak_source": peak_src}
         if "medoid" in timing:
             kern["medoid"]["pair_distances"] = pairs
             kern["medoid"]["gpairs_per_s"] = pairs / (timing["medoid"] * 1e-3) / 1e9
