@@ -339,3 +339,51 @@ def test_full_size_configs(lifter, cfg):
         got = sums[r.seg_offsets[i]:r.seg_offsets[i + 1]]
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (cfg, i, idx.size)
         assert r.medoid_local[i] == j or f.dataset == "kitti" and idx.size < 4
+
+
+def _check_vs_c_oracle(f, r):
+    from oracle import c_oracle as CO
+    o = CO.lift_frame_c(f, record_pix=False)
+    aggr = o["aggr"].T if f.dataset == "kitti" else o["aggr"]
+    assert r.n_points == o["n_points"]
+    if aggr.size:
+        assert np.array_equal(r.aggr_points[:aggr.shape[0]].view(np.uint32), np.ascontiguousarray(aggr).view(np.uint32))
+    for i in range(f.n_instances):
+        assert np.array_equal(r.instance_points(i), o["idx"][i]), (f.token, i)
+    assert np.array_equal(r.medoid_local, o["medoid_local"])
+    assert np.array_equal(r.medoid_point_idx, o["medoid_point_idx"])
+
+
+def test_edge_cases_overflow_many_instances_empty_and_generic_chain(lifter):
+    """One batch with: points inside 8 overlapping masks (hit-word overflow path, and the segment
+    buffers outgrow their default size -> capacity retry), 200 instances in a frame (k_compact's
+    general path), a frame without instances, an empty sweep, and a camera chain outside the
+    specialised signatures (generic projection path).  All bit-exact against the C oracle."""
+    from cm3d_b200 import synthetic as S
+    from cm3d_b200.frames import op_T
+    a = S.make_nuscenes_frame(9001, n_sweeps=2, pts_per_sweep=5000, n_inst=10, mask_div=2)
+    a.masks[:8] = 1                                   # eight full-image masks ...
+    a.cam_nums[:8] = 0                                # ... all on camera 0
+    b = S.make_nuscenes_frame(9002, n_sweeps=1, pts_per_sweep=20000, n_inst=200, mask_div=4)
+    c = S.make_nuscenes_frame(9003, n_sweeps=2, pts_per_sweep=3000, n_inst=0, mask_div=2)
+    d = S.make_nuscenes_frame(9004, n_sweeps=3, pts_per_sweep=3000, n_inst=6, mask_div=2)
+    d.sweeps[1] = d.sweeps[1][:0]                     # a sweep file with no points
+    e = S.make_kitti_frame(9005, n_pts=15000, n_inst=6, mask_div=2)
+    e.cams[0].ops = list(e.cams[0].ops) + [op_T(np.zeros(3))]       # A,A,R,T: no specialised kernel for it
+    frames = [a, b, c, d, e]
+    res = lifter.lift_frames(frames, with_points=True)
+    assert lifter.last.db.pb.table("frame_desc", 20)[4, 15] not in (153, 9, 47)
+    assert res[2].seg_offsets.tolist() == [0] and res[2].n_points > 0
+    assert (res[0].counts[:8] == res[0].counts[0]).all() and res[0].counts[0] > 100
+    for f, r in zip(frames, res):
+        _check_vs_c_oracle(f, r)
+
+
+def test_malformed_rle_raises(lifter):
+    from cm3d_b200 import synthetic as S
+    f = S.make_nuscenes_frame(9010, n_sweeps=1, pts_per_sweep=2000, n_inst=3, mask_div=2, dense_masks=False)
+    runs = np.asarray(f.masks[1].counts).copy()
+    runs[-1] += 7                                     # runs no longer sum to W*H
+    f.masks[1].counts = runs
+    with pytest.raises(ValueError):
+        lifter.lift_frames([f])
