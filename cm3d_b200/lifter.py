@@ -286,15 +286,28 @@ class Lifter:
         given, gets the wall time spent here under the reference's "points in mask" key."""
         import time
 
-        def batches():
+        def groups():
             cur = []
             for f in frames:
                 cur.append(f)
                 if len(cur) >= batch_frames:
-                    yield self.pack(cur)
+                    yield cur
                     cur = []
             if cur:
-                yield self.pack(cur)
+                yield cur
+
+        def batches():
+            # pack batch k+1 (numpy copies into pinned memory, GIL released) while batch k is on the GPU
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=1) as pool:
+                pending = None
+                for g in groups():
+                    nxt = pool.submit(self.pack, g)
+                    if pending is not None:
+                        yield pending.result()
+                    pending = nxt
+                if pending is not None:
+                    yield pending.result()
 
         t0 = time.time()
         for pb, do, lab in self.lift_packed_stream(batches(), depth=depth, with_handles=True):
