@@ -101,13 +101,14 @@ def lane_yaws_distances_and_coords(all_centroids, all_lane_pts, device="cuda:0")
     if m == 0:
         raise ValueError("attempt to get argmin of an empty sequence")      # numpy's error in the reference
     dev = torch.device(device)
-    cxy = torch.from_numpy(cent32[:, :2].astype(np.float64)).to(dev)
-    lxy = torch.from_numpy(lanes32[:, :2].astype(np.float64)).to(dev)
-    idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    dist = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
-    N.call("cm3d_nearest_lane", ctypes.c_void_p(cxy.data_ptr()), n, ctypes.c_void_p(lxy.data_ptr()), m,
-           ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(dist.data_ptr()),
-           ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    with torch.cuda.device(dev):                     # the C ABI launches on the current CUDA device
+        cxy = torch.from_numpy(cent32[:, :2].astype(np.float64)).to(dev)
+        lxy = torch.from_numpy(lanes32[:, :2].astype(np.float64)).to(dev)
+        idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        dist = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+        N.call("cm3d_nearest_lane", ctypes.c_void_p(cxy.data_ptr()), n, ctypes.c_void_p(lxy.data_ptr()), m,
+               ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(dist.data_ptr()),
+               ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     idx = idx[:n].cpu().numpy().astype(np.int64)
     return lanes32[idx, 2], dist[:n].cpu().numpy(), lanes32[idx, :2]
 

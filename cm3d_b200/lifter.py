@@ -58,6 +58,30 @@ class DeviceOutputs:
     seg_off_raw: Optional[torch.Tensor] = None   # (I+1,) offsets before the neighbour-count filter
 
 
+def _on_device(fn):
+    """Run a Lifter method with the lifter's GPU as the current CUDA device (generators included)."""
+    import functools
+    import inspect
+    if inspect.isgeneratorfunction(fn):
+        @functools.wraps(fn)
+        def gen(self, *a, **k):
+            it = fn(self, *a, **k)
+            while True:
+                with torch.cuda.device(self.device):
+                    try:
+                        item = next(it)
+                    except StopIteration:
+                        return
+                yield item
+        return gen
+
+    @functools.wraps(fn)
+    def call(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return call
+
+
 class Lifter:
     """One per process / GPU.  All methods enqueue on the current torch CUDA stream."""
 
@@ -65,6 +89,11 @@ class Lifter:
         if not torch.cuda.is_available():
             raise N.Cm3dError("cm3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        # one process per GPU: the C ABI launches on the CURRENT CUDA device, so make this one current
+        # (run()/upload()/the stream paths also guard it for callers that switch devices in between)
+        torch.cuda.set_device(self.device)
         self.seg_factor = float(seg_factor)
         N.load()
         self._streams = None        # (copy, compute) streams of the pipelined path, created once: torch's
@@ -90,6 +119,7 @@ class Lifter:
     def pack(self, frames: Sequence[FrameSpec]) -> PackedBatch:
         return pack_frames(frames, pin=True)
 
+    @_on_device
     def upload(self, pb: PackedBatch) -> DeviceBatch:
         def up(name, arr):
             t = pb.tensors.get(name)
@@ -111,6 +141,7 @@ class Lifter:
         lay["_words"] = pos
         return lay
 
+    @_on_device
     def run(self, db: DeviceBatch, seg_cap: Optional[int] = None, want_pix: bool = False,
             want_col_sums: bool = False, do_medoid: bool = True, want_obb: Optional[bool] = None,
             denoise=None, box_search: Optional[int] = None) -> DeviceOutputs:
@@ -256,6 +287,7 @@ class Lifter:
                              pix, col_sums, hits, bits, bbox, obb, box, seg_off_raw)
 
     # ------------------------------------------------------------------ device -> host
+    @_on_device
     def fetch_labels(self, do: DeviceOutputs, pinned: Optional[torch.Tensor] = None) -> dict:
         """D2H of the small per-instance result block (sizes, medoids, centroids, flags)."""
         if pinned is not None:
@@ -278,6 +310,7 @@ class Lifter:
         res["centroid"] = res["centroid"].view(np.float32).reshape(-1, 4)
         return res
 
+    @_on_device
     def lift_frame_stream(self, frames, batch_frames: int = 32, timer: Optional[dict] = None, depth: int = 2):
         """Drop-in scripts' entry: an iterator of FrameSpecs in, lists of LiftResult (one list per
         batch of `batch_frames` frames, frame order kept) out.  Batches are packed into pinned
@@ -317,6 +350,7 @@ class Lifter:
             yield res
             t0 = time.time()
 
+    @_on_device
     def lift_packed_stream(self, batches, seg_cap: Optional[int] = None, depth: int = 2, with_handles: bool = False):
         """Pipelined bulk path (config C5: tens of thousands of frames): yields the label dict of
         every PackedBatch in order.  Batch k+1 is copied host->device on a copy stream while batch
@@ -374,6 +408,7 @@ class Lifter:
             raise ValueError(f"instance {int(e[1]) - 1}: COCO run lengths do not cover the mask")
         return int(e[0])            # members needed when the segment buffers were too small, else 0
 
+    @_on_device
     def results(self, do: DeviceOutputs, labels: dict, with_points: bool = True, with_pix: bool = False) -> List[LiftResult]:
         pb = do.db.pb
         seg_off = labels["seg_off"].astype(np.int64)
@@ -415,6 +450,7 @@ class Lifter:
             out.append(r)
         return out
 
+    @_on_device
     def lift_frames(self, frames: Sequence[FrameSpec], with_points: bool = True, with_pix: bool = False,
                     want_col_sums: bool = False, denoise=None, box_search: Optional[int] = None) -> List[LiftResult]:
         """Synchronous convenience: pack, upload, run, read back; retries once with exact

@@ -177,7 +177,8 @@ def waymo_frames(scene_name: str, input_dir: str, frames: List[FrameSpec], ratio
     """Duck-typed `dataset_pb2.Frame`s: .context.name/.camera_calibrations[].name/.extrinsic.transform/
     .intrinsic, .pose.transform, .timestamp_micros, .map_features, plus `.points_vehicle` (N,3) standing
     in for `convert_range_image_to_point_cloud(...)[0]` (waymo/2d_to_3d.py:472-476)."""
-    rng = np.random.default_rng(hash(scene_name) % (2 ** 31))
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(scene_name.encode()))      # stable across processes (str hash is salted)
     axes = np.array([[0, -1, 0, 0], [0, 0, -1, 0], [1, 0, 0, 0], [0, 0, 0, 1]], np.float64)
     out = []
     yaw0 = rng.uniform(-np.pi, np.pi)

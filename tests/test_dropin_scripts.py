@@ -219,3 +219,25 @@ def test_waymo_script_matches_oracle(tmp_path):
         for k in ("center_x", "center_y", "center_z"):
             assert abs(g[k] - e[k]) < 1e-3                 # fp32 pose arithmetic vs fp64 restatement: 1e-3 m
         assert abs(((g["heading"] - e["heading"] + np.pi) % (2 * np.pi)) - np.pi) < 1e-3
+
+
+@pytest.mark.gpu
+def test_scripts_sharded_over_two_gpus_match_single_process(tmp_path):
+    """`torchrun --nproc-per-node 2` over the three scripts (scenes / frames sharded by index, one
+    process per GPU, host-side gather) writes byte-identical label files to a single process."""
+    import filecmp
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    tool = os.path.join(ROOT, "tools", "run_synthetic_scripts.py")
+    a, b = str(tmp_path / "one"), str(tmp_path / "two")
+    subprocess.run([sys.executable, tool, "--out", a], check=True, capture_output=True, timeout=600)
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                    "--master-addr", "127.0.0.1", "--master-port", "29541", tool, "--out", b],
+                   check=True, capture_output=True, timeout=600)
+    rels = ["nuscenes/pseudolabels_minival.json", "waymo/pred.bin"] + \
+           [f"kitti/{d}/{f:06}.txt" for d in ("pred", "pseudo") for f in range(5)]
+    for rel in rels:
+        assert os.path.getsize(os.path.join(a, rel)) > 0, rel
+        assert filecmp.cmp(os.path.join(a, rel), os.path.join(b, rel), shallow=False), rel
