@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .batch import ERR_WORDS, FR_WORDS, MEDOID_COLS, TILE, PackedBatch, pack_frames
+from .batch import ERR_WORDS, FR_WORDS, MAX_INST, MEDOID_COLS, TILE, PackedBatch, pack_frames
 from .frames import FrameSpec, LiftResult
 
 
@@ -56,6 +56,53 @@ class DeviceOutputs:
     obb: Optional[torch.Tensor] = None     # (I,16): yaw, centre, wlh, R' (KITTI frames / want_obb)
     box: Optional[torch.Tensor] = None     # (I,8): orientation search (box_search=n_angles)
     seg_off_raw: Optional[torch.Tensor] = None   # (I+1,) offsets before the neighbour-count filter
+
+
+def split_oversize(frames: Sequence[FrameSpec], limit: int):
+    """Frames with more than `limit` instances (the kernels keep instance ids in one byte) are split
+    into sub-frames over the same sweeps and cameras with disjoint instance ranges; the reference has
+    no such limit.  Returns (flat list of frames, parts) with parts[k] = number of sub-frames of input k."""
+    import copy
+    flat, parts = [], []
+    for f in frames:
+        n = f.n_instances
+        if n <= limit:
+            flat.append(f)
+            parts.append(1)
+            continue
+        k = -(-n // limit)
+        for a in range(0, n, limit):
+            g = copy.copy(f)
+            sl = slice(a, min(a + limit, n))
+            g.cam_nums = f.cam_nums[sl]
+            g.masks = f.masks[sl]
+            g.labels = list(f.labels[sl])
+            g.scores = list(f.scores[sl])
+            flat.append(g)
+        parts.append(k)
+    return flat, parts
+
+
+def merge_split(results: List[LiftResult], parts: Sequence[int]) -> List[LiftResult]:
+    out, p = [], 0
+    for k in parts:
+        grp = results[p:p + k]
+        p += k
+        if k == 1:
+            out.append(grp[0])
+            continue
+        cat = lambda name: (None if getattr(grp[0], name) is None else np.concatenate([getattr(g, name) for g in grp]))
+        offs, base = [np.zeros(1, np.int32)], 0
+        for g in grp:
+            offs.append(g.seg_offsets[1:] + base)
+            base += int(g.seg_offsets[-1])
+        r = LiftResult(n_points=grp[0].n_points, seg_offsets=np.concatenate(offs).astype(np.int32),
+                       seg_point_idx=cat("seg_point_idx"), medoid_local=cat("medoid_local"),
+                       medoid_point_idx=cat("medoid_point_idx"), centroids=cat("centroids"),
+                       aggr_points=grp[0].aggr_points, pix=None, yaw=cat("yaw"), obb=cat("obb"), box=cat("box"),
+                       raw_counts=cat("raw_counts"))
+        out.append(r)
+    return out
 
 
 def _on_device(fn):
@@ -319,14 +366,20 @@ class Lifter:
         given, gets the wall time spent here under the reference's "points in mask" key."""
         import time
 
+        part_queue = []                         # per batch: sub-frame counts of its (possibly split) frames
+
         def groups():
-            cur = []
+            cur, parts = [], []
             for f in frames:
-                cur.append(f)
-                if len(cur) >= batch_frames:
+                sub, k = split_oversize([f], MAX_INST)
+                cur.extend(sub)
+                parts.extend(k)
+                if len(parts) >= batch_frames:
+                    part_queue.append(parts)
                     yield cur
-                    cur = []
+                    cur, parts = [], []
             if cur:
+                part_queue.append(parts)
                 yield cur
 
         def batches():
@@ -344,7 +397,7 @@ class Lifter:
 
         t0 = time.time()
         for pb, do, lab in self.lift_packed_stream(batches(), depth=depth, with_handles=True):
-            res = self.results(do, lab, with_points=False)
+            res = merge_split(self.results(do, lab, with_points=False), part_queue.pop(0))
             if timer is not None:
                 timer["points in mask"] += time.time() - t0
             yield res
@@ -455,6 +508,7 @@ class Lifter:
                     want_col_sums: bool = False, denoise=None, box_search: Optional[int] = None) -> List[LiftResult]:
         """Synchronous convenience: pack, upload, run, read back; retries once with exact
         segment capacity if the default guess was too small."""
+        frames, parts = split_oversize(frames, MAX_INST)
         pb = self.pack(frames)
         db = self.upload(pb)
         kw = dict(want_pix=with_pix, want_col_sums=want_col_sums, denoise=denoise, box_search=box_search)
@@ -468,4 +522,4 @@ class Lifter:
                 raise N.Cm3dError("segment capacity retry failed")
         res = self.results(do, labels, with_points, with_pix)
         self.last = do
-        return res
+        return merge_split(res, parts) if any(k > 1 for k in parts) else res

@@ -387,3 +387,20 @@ def test_malformed_rle_raises(lifter):
     f.masks[1].counts = runs
     with pytest.raises(ValueError):
         lifter.lift_frames([f])
+
+
+def test_more_than_254_instances_are_split_and_merged(lifter):
+    """The reference has no instance limit; the kernels keep ids in a byte, so the host splits a
+    600-instance frame into three sub-frames over the same cloud and merges the labels."""
+    from cm3d_b200 import synthetic as S
+    f = S.make_nuscenes_frame(9020, n_sweeps=1, pts_per_sweep=15000, n_inst=600, mask_div=4)
+    small = S.make_nuscenes_frame(9021, n_sweeps=1, pts_per_sweep=4000, n_inst=5, mask_div=4)
+    res = lifter.lift_frames([f, small], with_points=True)
+    assert len(res) == 2 and len(res[0].medoid_local) == 600 and len(res[1].medoid_local) == 5
+    for fr, r in zip([f, small], res):
+        _check_vs_c_oracle(fr, r)
+    # the streaming entry point merges too
+    out = [r for batch in lifter.lift_frame_stream(iter([small, f, small]), batch_frames=2) for r in batch]
+    assert [len(r.medoid_local) for r in out] == [5, 600, 5]
+    assert np.array_equal(out[1].medoid_point_idx, res[0].medoid_point_idx)
+    assert np.array_equal(out[1].counts, res[0].counts)
