@@ -343,8 +343,9 @@ def test_full_size_configs(lifter, cfg):
 
 def _check_vs_c_oracle(f, r):
     from oracle import c_oracle as CO
+    from cm3d_b200.frames import FOURTH_NONE
     o = CO.lift_frame_c(f, record_pix=False)
-    aggr = o["aggr"].T if f.dataset == "kitti" else o["aggr"]
+    aggr = o["aggr"].T if f.fourth == FOURTH_NONE else o["aggr"]      # 3-row clouds come back as (N,3) rows
     assert r.n_points == o["n_points"]
     if aggr.size:
         assert np.array_equal(r.aggr_points[:aggr.shape[0]].view(np.uint32), np.ascontiguousarray(aggr).view(np.uint32))
@@ -404,3 +405,70 @@ def test_more_than_254_instances_are_split_and_merged(lifter):
     assert [len(r.medoid_local) for r in out] == [5, 600, 5]
     assert np.array_equal(out[1].medoid_point_idx, res[0].medoid_point_idx)
     assert np.array_equal(out[1].counts, res[0].counts)
+
+
+def _random_frame(rng, k):
+    """A small frame with arbitrary geometry: random rigid chains of every kind mix, random (also
+    skewed / non-pinhole-normalised) intrinsics, random blob masks, points all around the sensor."""
+    from scipy.spatial.transform import Rotation
+    from cm3d_b200.frames import CamSpec, FrameSpec, FOURTH_COL3, FOURTH_NONE, FOURTH_ONES, op_A, op_R, op_T
+    rot = lambda: Rotation.random(random_state=int(rng.integers(1 << 30))).as_matrix()
+    n_sweeps = int(rng.integers(1, 4))
+    stride = int(rng.choice([3, 4, 5]))
+    far = float(rng.choice([0.0, 1500.0]))                     # nuScenes-like global offsets or sensor frame
+    t_world = rng.uniform(-1, 1, 3) * far
+    sweeps, sweep_ops = [], []
+    for s in range(n_sweeps):
+        n = int(rng.integers(0, 3000))
+        r = np.exp(rng.uniform(np.log(0.5), np.log(60.0), n))
+        az, el = rng.uniform(-np.pi, np.pi, n), rng.uniform(-0.5, 0.3, n)
+        p = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el)], 1)
+        raw = np.concatenate([p, rng.uniform(0, 255, (n, stride - 3))], 1).astype(np.float32)
+        sweeps.append(raw)
+        kind = int(rng.integers(0, 4))
+        Rs = rot() if rng.random() < 0.5 else np.eye(3)
+        sweep_ops.append([[], [op_R(Rs), op_T(t_world)], [op_A(np.concatenate([Rs, t_world[:, None]], 1))],
+                          [op_R(Rs), op_T(rng.uniform(-1, 1, 3)), op_R(np.eye(3)), op_T(t_world)]][kind])
+    n_cams = int(rng.integers(1, 5))
+    W, H = int(rng.integers(64, 400)), int(rng.integers(48, 300))
+    cams = []
+    for c in range(n_cams):
+        Rc, tc = rot(), rng.uniform(-2, 2, 3)
+        kind = int(rng.integers(0, 5))
+        ops = [[op_T(-t_world), op_R(np.eye(3)), op_T(-tc), op_R(Rc.T)], [op_T(-t_world - tc), op_R(Rc.T)],
+               [op_A(np.concatenate([Rc.T, (-Rc.T @ (t_world + tc))[:, None]], 1))],
+               [op_R(Rc.T), op_T(-Rc.T @ (t_world + tc))], [op_T(-t_world), op_A(np.concatenate([Rc.T, (-Rc.T @ tc)[:, None]], 1)), op_R(np.eye(3))]][kind]
+        f = rng.uniform(0.4, 2.0) * W
+        K = np.array([[f, 0, rng.uniform(0.3, 0.7) * W], [0, f * rng.uniform(0.9, 1.1), rng.uniform(0.3, 0.7) * H], [0, 0, 1]])
+        style = rng.random()
+        if style < 0.2:
+            K[0, 1] = rng.uniform(-0.05, 0.05) * f             # skew: generic viewpad path
+        elif style < 0.3:
+            K[2, 2] = 1.0
+            K[2, 0] = 1e-4                                     # not a pinhole third row: cull planes disabled
+        cams.append(CamSpec(ops, K.astype(np.float32)))
+    n_inst = int(rng.integers(0, 12))
+    masks = np.zeros((n_inst, H, W), np.uint8)
+    for i in range(n_inst):
+        for _ in range(int(rng.integers(1, 4))):
+            x0, y0 = int(rng.integers(0, W)), int(rng.integers(0, H))
+            masks[i, max(0, y0 - int(rng.integers(1, H))):y0 + 1, max(0, x0 - int(rng.integers(1, W))):x0 + 1] = 1
+    fourth = FOURTH_NONE if stride == 3 and rng.random() < 0.5 else (FOURTH_ONES if stride == 3 else int(rng.choice([FOURTH_COL3, FOURTH_ONES, FOURTH_NONE])))
+    return FrameSpec(str(rng.choice(["nuscenes", "waymo"])), sweeps, sweep_ops, cams, rng.integers(0, n_cams, n_inst), masks,
+                     ["car"] * n_inst, [0.5] * n_inst, fourth=fourth,
+                     close_thresh=(float(np.float32(np.sqrt(2.3))) if rng.random() < 0.5 else None),
+                     min_dist=float(rng.choice([2.3, 0.5, 5.0])), token=f"random-{k}")
+
+
+def test_randomised_geometry_against_c_oracle(lifter):
+    """60 random frames (chain kinds, intrinsics incl. skew and non-pinhole rows, empty sweeps, random
+    blob masks, 3/4/5-column sweeps, with/without the close filter) in 6 batches: bit-exact."""
+    rng = np.random.default_rng(20261018)
+    frames = [_random_frame(rng, k) for k in range(60)]
+    n_member = 0
+    for b in range(0, 60, 10):
+        res = lifter.lift_frames(frames[b:b + 10], with_points=True)
+        for f, r in zip(frames[b:b + 10], res):
+            _check_vs_c_oracle(f, r)
+            n_member += int(r.seg_offsets[-1])
+    assert n_member > 3000
