@@ -141,3 +141,67 @@ def test_waymo_objects_wire_format_matches_protobuf_library():
         assert a["width"] == c.object.box.width and a["heading"] == b["heading"] == c.object.box.heading
         assert b["score"] == c.score == np.float32(a["score"]) and a["type"] == b["type"] == c.object.type
         assert c.object.id == "unique object tracking ID"
+
+
+def _members(frame):
+    from oracle import c_oracle as CO
+    o = CO.lift_frame_c(frame, record_pix=False, do_medoid=False)
+    return o["n_points"], [len(x) for x in o["idx"]]
+
+
+def test_stage_frame_specs_from_on_disk_datasets(tmp_path):
+    """Host logic of the three scripts without a GPU: the FrameSpecs they build from the on-disk
+    layouts (devkit-style tables + quaternions, KITTI calib files, Waymo calibration protos, masks as
+    pycocotools strings in `{f}_masks.pkl`) see the same points in the same masks as the frames the
+    datasets were written from."""
+    from cm3d_b200 import kitti_stage, nuscenes_stage, waymo_stage
+    from cm3d_b200 import synthetic as S
+    from cm3d_b200 import synthetic_datasets as SD
+    # nuScenes: quaternion round trip + `next` chain + KeyError at the end of the sweep chain
+    fr = [S.make_nuscenes_frame(7100 + f, n_sweeps=2, pts_per_sweep=4000, n_inst=8, mask_div=2, dense_masks=False) for f in range(2)]
+    nusc, mf = SD.write_nuscenes(str(tmp_path / "n"), str(tmp_path / "nm"), {"scene-0001": fr}, ratio=0.32)
+    cfg = nuscenes_stage.make_cfg(INPUT_DIR=str(tmp_path / "nm"), ratio=0.32, n_sweeps=3)      # asks for 3, chain has 2
+    scene = nusc.get("scene", nusc.field2token("scene", "name", "scene-0001")[0])
+    sample = nusc.get("sample", scene["first_sample_token"])
+    assert nuscenes_stage.count_frames(nusc, sample) == 2
+    for f in range(2):
+        masks, data = nuscenes_stage.load_frame_masks(str(tmp_path / "nm"), "scene-0001", f)
+        assert isinstance(masks[0].counts, bytes) and data["cam_nums"] == [int(c) for c in fr[f].cam_nums]
+        spec = nuscenes_stage.frame_spec(nusc, sample, masks, data, cfg)
+        assert len(spec.sweeps) == 2 and spec.sweeps[0].shape[1] == 5 and spec.token == sample["token"]
+        assert _members(spec) == _members(fr[f])
+        if sample["next"]:
+            sample = nusc.get("sample", sample["next"])
+    _, lanes = nuscenes_stage.get_all_lane_points_in_scene(mf(nusc, scene))
+    assert len(lanes) > 100 and len(lanes[0]) == 3
+    # KITTI: calib text -> Calibration -> chains
+    kf = [S.make_kitti_frame(8300, n_pts=8000, n_inst=6, mask_div=1, dense_masks=False)]
+    SD.write_kitti(str(tmp_path / "k"), str(tmp_path / "km"), kf)
+    kcfg = kitti_stage.make_cfg(INPUT_PATH=str(tmp_path / "k"), INPUT_DIR=str(tmp_path / "km"), num_samples=1)
+    kitti = kitti_stage.kitti_object(str(tmp_path / "k"), "training", 1)
+    assert len(kitti) == 1 and len(kitti_stage.kitti_object(str(tmp_path / "k"))) == 7481
+    masks, data = kitti_stage.load_frame_masks(str(tmp_path / "km"), None, 0)
+    assert "cam_nums" not in data
+    assert _members(kitti_stage.frame_spec(kitti, 0, masks, data, kcfg)) == _members(kf[0])
+    # Waymo: extrinsic . inv(axes) -> scipy quaternion -> pyquaternion matrix; fp64 intrinsics
+    wf = [S.make_waymo_frame(8400, n_pts=8000, n_inst=10, mask_div=2)]
+    frames = SD.waymo_frames("segment-x", str(tmp_path / "wm"), wf, ratio=(1024 / 1920) / 2)
+    wcfg = waymo_stage.make_cfg(INPUT_DIR=str(tmp_path / "wm"), ratio=(1024 / 1920) / 2)
+    masks, data = waymo_stage.load_frame_masks(str(tmp_path / "wm"), "segment-x", 0)
+    spec = waymo_stage.frame_spec(frames[0], masks, data, wcfg, lambda f: f.points_vehicle)
+    n0, m0 = _members(wf[0])
+    n1, m1 = _members(spec)
+    assert n0 == n1 and sum(abs(a - b) for a, b in zip(m0, m1)) <= 0.01 * sum(m0)     # matrices differ in the last bits
+    lanes = waymo_stage.lanes_of_frame(frames[0])
+    assert lanes.shape[1] == 3 and lanes[0, 2] == lanes[1, 2]                          # vertex 0 copies vertex 1's yaw
+    g = waymo_stage.centroid_to_global(np.array([10.0, 2.0, 1.0, 1.0], np.float32), frames[0])
+    assert np.allclose(g, RB.waymo_centroid_to_global([10.0, 2.0, 1.0], frames[0].pose.transform), atol=1e-3)
+
+
+def test_kitti_label_line_format(tmp_path):
+    from cm3d_b200 import kitti_stage
+    p = str(tmp_path / "000007.txt")
+    kitti_stage.save_pred(p, "Car", [0, 0, 0, 0], [1.4, 1.8, 4.5], [1.0, 2.5, 30.0], -1.5, 0.75)
+    kitti_stage.save_pred(p, "Cyclist", [0, 0, 0, 0], [1.4, 0.6, 1.8], [1.0, 2.5, 30.0], 0.25, None)
+    assert open(p).read() == ("Car -1 -1 -10 0 0 0 0 1.4 1.8 4.5 1.0 2.5 30.0 -1.5 0.75\n"
+                              "Cyclist -1 -1 -10 0 0 0 0 1.4 0.6 1.8 1.0 2.5 30.0 0.25\n")
