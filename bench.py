@@ -254,7 +254,9 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    do = None
     for _ in range(args.steps):
+        del do                          # free the previous step's buffers first: no second workspace, no cudaMalloc
         do = lifter.run(db, seg_cap=seg_cap)
     e1.record()
     barrier()

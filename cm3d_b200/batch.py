@@ -25,6 +25,7 @@ TILE = 1024
 MAX_INST = 254
 MAX_VCAMS = 16
 MEDOID_COLS = 256
+SCREEN_MIN_PTS = 512          # CM3D_SCREEN_MIN_PTS: medoid instances this large are screened, then verified
 CELL = 32
 SW_WORDS, FR_WORDS, VC_WORDS, IN_WORDS, ERR_WORDS = 8, 20, 44, 8, 4
 

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .batch import ERR_WORDS, FR_WORDS, MAX_INST, MEDOID_COLS, TILE, PackedBatch, pack_frames
+from .batch import ERR_WORDS, FR_WORDS, MAX_INST, MEDOID_COLS, SCREEN_MIN_PTS, TILE, PackedBatch, pack_frames
 from .frames import FrameSpec, LiftResult
 
 
@@ -149,6 +149,8 @@ class Lifter:
         self.denoise = None         # default-off extensions, see run()
         self.box_search = None
         self.launches = 0           # kernels launched by this object (bench.py reports it)
+        self.screen_min_pts = SCREEN_MIN_PTS   # medoid: instances this large are screened, then verified; 0 = all exact
+        self.last_screen_stats = None          # device int32[1]: columns the last run() verified exactly
         self.timing = None          # dict label -> [(start_event, end_event)] when bench.py profiles
 
     def _call(self, label: str, name: str, *args):
@@ -303,14 +305,22 @@ class Lifter:
             o("seg_off")[:I + 1].copy_(seg_off2[:I + 1])
             seg_point_idx, seg_xyzw = seg_point_idx2, seg_xyzw2
 
-        # ---- medoid
+        # ---- medoid (screen + verify for instances of >= screen_min_pts points, see csrc/medoid.cu)
         col_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if want_col_sums else None
+        screen_stats = None
         if do_medoid and I:
             max_items = seg_cap // MEDOID_COLS + 2 * I
+            screen = self.screen_min_pts > 0 and not want_col_sums
+            screen_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if screen else None
+            screen_min = torch.empty(I, **i32) if screen else None
+            screen_stats = torch.zeros(1, **i32) if screen else None
+            item_pos = torch.empty(max_items, **i32)
             self._call("medoid", "cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), _ptr(seg_point_idx),
-                   _ptr(o("item_off")), _ptr(item_inst), I, max_items, _ptr(medoid_best), _ptr(col_sums), _ptr(o("medoid_local")),
-                   _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
-            self.launches += 2
+                   _ptr(o("item_off")), _ptr(item_inst), I, max_items, _ptr(medoid_best), _ptr(col_sums),
+                   _ptr(screen_sums), _ptr(screen_min), int(self.screen_min_pts) if screen else 0, _ptr(screen_stats), _ptr(item_pos),
+                   _ptr(o("medoid_local")), _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
+            self.launches += 6 if screen else 3
+        self.last_screen_stats = screen_stats
         # ---- KITTI: principal-axes box + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479)
         obb = None
         if want_obb is None:

@@ -178,6 +178,7 @@ def test_small_segments_all_sizes(lifter):
     p = lambda x: ctypes.c_void_p(x.data_ptr())
     d_inst = torch.arange(n, dtype=torch.int32, device=dev)
     N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), p(d_inst), n, int(item_off[-1]) + 3, p(best), p(col),
+           None, None, 0, None, None,
            p(ml), p(mp), p(cen), p(err), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     col, ml = col.cpu().numpy(), ml.cpu().numpy()
@@ -186,6 +187,124 @@ def test_small_segments_all_sizes(lifter):
         got = col[seg_off[k]:seg_off[k + 1]]
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), m
         assert ml[k] == j, m
+
+
+def _medoid_abi(pts_list, screen_min_pts, want_sums=False):
+    """cm3d_medoid on hand-made segments (list of (3,M) fp32) through the C ABI.
+    Returns (medoid_local, column sums or None, verified-column count)."""
+    import torch, ctypes
+    from cm3d_b200 import _native as N
+    sizes = [q.shape[1] for q in pts_list]
+    seg_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    cap = int(seg_off[-1] + 3) & ~3
+    xyzw = np.zeros((4, cap), np.float32)
+    xyzw[:3, :seg_off[-1]] = np.concatenate(pts_list, 1)
+    items = [N.load().cm3d_medoid_items(int(m), 1) for m in sizes]
+    item_off = np.concatenate([[0], np.cumsum(items)]).astype(np.int32)
+    dev = "cuda:0"
+    t = lambda a: torch.from_numpy(a).to(dev)
+    d_xyzw, d_off, d_item = t(xyzw.reshape(-1)), t(seg_off), t(item_off)
+    d_idx = torch.arange(cap, dtype=torch.int32, device=dev)
+    n = len(sizes)
+    best = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    col = torch.zeros(cap, dtype=torch.float32, device=dev) if want_sums else None
+    ssum = torch.zeros(cap, dtype=torch.float32, device=dev)
+    smin = torch.zeros(n, dtype=torch.int32, device=dev)
+    stats = torch.zeros(1, dtype=torch.int32, device=dev)
+    ipos = torch.zeros(int(item_off[-1]) + 3, dtype=torch.int32, device=dev) if screen_min_pts != 32 else None
+    ml = torch.zeros(n, dtype=torch.int32, device=dev)
+    mp = torch.zeros(n, dtype=torch.int32, device=dev)
+    cen = torch.zeros(4 * n, dtype=torch.float32, device=dev)
+    err = torch.zeros(4, dtype=torch.int32, device=dev)
+    p = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None else None
+    d_inst = torch.arange(n, dtype=torch.int32, device=dev)
+    N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), p(d_inst), n, int(item_off[-1]) + 3, p(best), p(col),
+           p(ssum), p(smin), int(screen_min_pts), p(stats), p(ipos),
+           p(ml), p(mp), p(cen), p(err), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    sums = None
+    if want_sums:
+        c = col.cpu().numpy()
+        sums = [c[seg_off[k]:seg_off[k + 1]] for k in range(n)]
+    return ml.cpu().numpy(), sums, int(stats.item())
+
+
+def _screen_cases():
+    rng = np.random.default_rng(7)
+    ctr = np.array([[1200.0], [950.0], [1.0]])
+    cases = []
+    # every size class around the item / tile / cascade boundaries, global-frame coordinates
+    for m in [32, 33, 47, 63, 64, 65, 95, 96, 97, 255, 256, 257, 287, 288, 289, 511, 512, 513, 1023, 1024, 1025,
+              1039, 1040, 1041, 1279, 1280, 1281, 2047, 2048, 2077, 4095, 4096, 4097, 4111, 4112, 4113, 4351,
+              4352, 4353, 5000, 8191, 8192, 8193, 8208, 12289]:
+        cases.append((rng.normal(0, 3, (3, m)) + ctr).astype(np.float32))
+    # local-frame coordinates (KITTI / Waymo magnitude): little cancellation noise
+    for m in [100, 777, 3000, 4100]:
+        cases.append(rng.normal(0, 2, (3, m)).astype(np.float32) + np.float32(10.0))
+    # ties: every point identical; two distinct points; a small lattice repeated many times
+    cases.append(np.repeat((ctr + 0.5).astype(np.float32), 700, axis=1))
+    cases.append(np.repeat(np.array([[1.0, 2.0], [3.0, 3.0], [0.5, 0.5]], np.float32), 400, axis=1))
+    g = np.stack(np.meshgrid(np.arange(6.0), np.arange(6.0), np.arange(3.0)), 0).reshape(3, -1)
+    cases.append(np.tile(g, (1, 12)).astype(np.float32) + np.float32(300.0))
+    cases.append(rng.permuted(np.tile(g, (1, 20)), axis=1).astype(np.float32) * np.float32(0.25) + np.float32(1800.0))
+    # near ties: points on a circle (every column sum almost equal), with and without the centre
+    th = np.linspace(0, 2 * np.pi, 1500, endpoint=False)
+    ring = np.stack([1000.0 + 5 * np.cos(th), 700.0 + 5 * np.sin(th), np.zeros_like(th)]).astype(np.float32)
+    cases.append(ring)
+    cases.append(np.concatenate([ring, np.array([[1000.0], [700.0], [0.0]], np.float32)], 1))
+    # the medoid in the tail columns: a tight clump placed last, the rest far around it
+    far = (rng.normal(0, 20, (3, 1000)) + ctr).astype(np.float32)
+    clump = (rng.normal(0, 0.01, (3, 7)) + ctr).astype(np.float32)
+    cases.append(np.concatenate([far, clump], 1))
+    # zeros among the coordinates (allowed by the range check) and an out-of-range instance (exact path)
+    z = (rng.normal(0, 3, (3, 900))).astype(np.float32); z[2, ::3] = 0.0
+    cases.append(z)
+    tiny = (rng.normal(0, 3, (3, 600))).astype(np.float32); tiny[0, 5] = 1e-30
+    cases.append(tiny)                                   # one tiny coordinate: still screened (|p|^2 is large)
+    org = (rng.normal(0, 3, (3, 640))).astype(np.float32); org[:, 9] = 0.0
+    cases.append(org)                                    # a point at the exact origin: screened
+    sub = (rng.normal(0, 3, (3, 600))).astype(np.float32); sub[:, 5] = (1e-25, 0.0, -2e-24)
+    cases.append(sub)                                    # |p|^2 underflows: NOT screened, exact path
+    return cases
+
+
+def test_medoid_screen_equals_exact(lifter):
+    """Screen + verify returns the medoid of the all-exact kernel (and of the C oracle) on every size
+    class, on ties / near ties (first minimum), on tail-column medoids and on range-check fallbacks;
+    the screen is forced down to 32-point instances and run at its default threshold."""
+    from oracle import c_oracle as CO
+    cases = _screen_cases()
+    exact, sums, _ = _medoid_abi(cases, 0, want_sums=True)
+    for k, pts in enumerate(cases):
+        assert exact[k] == int(np.argmin(sums[k])), pts.shape           # first minimum of the exact sums
+    for k in list(range(0, len(cases), 5)) + list(range(len(cases) - 12, len(cases))):
+        j, ref = CO.medoid(cases[k], want_sums=True)
+        assert np.array_equal(sums[k].view(np.uint32), ref.view(np.uint32)) and exact[k] == j
+    for thr in (32, 512):
+        got, _, verified = _medoid_abi(cases, thr)
+        assert np.array_equal(got, exact), (thr, np.nonzero(got != exact)[0])
+        assert verified >= sum(1 for c in cases if c.shape[1] >= thr) - 1     # the out-of-range instance is not screened
+    # random segments: the screen leaves about one candidate per instance
+    rng = np.random.default_rng(11)
+    rnd = [(rng.normal(0, 2, (3, int(m))) + np.array([[900.0], [1500.0], [2.0]])).astype(np.float32)
+           for m in rng.integers(600, 6000, 40)]
+    exact, _, _ = _medoid_abi(rnd, 0)
+    got, _, verified = _medoid_abi(rnd, 512)
+    assert np.array_equal(got, exact)
+    assert len(rnd) <= verified <= 4 * len(rnd), verified
+
+
+def test_screen_sqrt_error_exhaustive(lifter):
+    """MUFU.SQRT vs IEEE sqrt.rn over every float of the screen's domain: the error bound in
+    csrc/medoid.cu assumes <= 4 ulp."""
+    import ctypes
+    import torch
+    from cm3d_b200 import _native as N
+    worst = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+    N.call("cm3d_selftest_sqrt_approx", ctypes.c_void_p(worst.data_ptr()),
+           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert 0 <= int(worst.item()) <= 2, int(worst.item())
 
 
 def test_fast_sqrt_exhaustive(lifter):

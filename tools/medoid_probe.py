@@ -15,13 +15,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cm3d_b200 import _native as N  # noqa: E402
 
 
-def run_case(name, sizes, reps=3, centre=(1200.0, 950.0, 1.0), order_desc=False):
+def run_case(name, sizes, reps=3, centre=(1200.0, 950.0, 1.0), order_desc=False, tiny_in=0):
     rng = np.random.default_rng(0)
     sizes = np.asarray(sizes, np.int64)
     seg_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     cap = (int(seg_off[-1]) + 3) & ~3
     xyzw = np.zeros((4, cap), np.float32)
     xyzw[:3, :seg_off[-1]] = (rng.normal(0, 3, (3, int(seg_off[-1]))) + np.array(centre)[:, None]).astype(np.float32)
+    for k in range(tiny_in):                 # a coordinate below 2^-20 in the first instances: range-check fallback
+        xyzw[2, seg_off[k] + 3] = 1e-9
     items = np.array([N.load().cm3d_medoid_items(int(m), 1) for m in sizes])
     if order_desc:
         order = np.argsort(-items, kind="stable").astype(np.int32)
@@ -42,11 +44,15 @@ def run_case(name, sizes, reps=3, centre=(1200.0, 950.0, 1.0), order_desc=False)
     err = torch.zeros(4, dtype=torch.int32, device=dev)
     p = lambda x: ctypes.c_void_p(x.data_ptr())
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ssum = torch.zeros(cap, dtype=torch.float32, device=dev)
+    smin = torch.zeros(n, dtype=torch.int32, device=dev)
+    ipos = torch.zeros(int(item_off[-1]) + 1, dtype=torch.int32, device=dev)
+    screen = int(os.environ.get("CM3D_SCREEN_MIN_PTS", "512"))
 
     def launch():
         best.fill_(-1)
         N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), p(d_inst), n, int(item_off[-1]), p(best),
-               ctypes.c_void_p(0), p(ml), p(mp), p(cen), p(err), st)
+               None, p(ssum), p(smin), screen, None, p(ipos), p(ml), p(mp), p(cen), p(err), st)
     launch()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -63,7 +69,19 @@ def run_case(name, sizes, reps=3, centre=(1200.0, 950.0, 1.0), order_desc=False)
     return ml.cpu().numpy()
 
 
+def split_cases():
+    """Which part of the screened medoid pays for what (run under `ncu --metrics gpu__time_duration.sum`)."""
+    big = [2976] * 3000
+    run_case("A 3000 x M=2976", big, reps=1, order_desc=True)
+    run_case("B A + 300 x M=300", big + [300] * 300, reps=1, order_desc=True)
+    run_case("C A + 300 x M=20", big + [20] * 300, reps=1, order_desc=True)
+    run_case("D A, 8 instances fail the range check", big, reps=1, order_desc=True, tiny_in=8)
+    run_case("E 300 x M=8000, 4 fail the range check", [8000] * 300, reps=1, order_desc=True, tiny_in=4)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "split":
+        return split_cases()
     rng = np.random.default_rng(1)
     run_case("592 x M=4096 (no tails, full blocks)", [4096] * 592)
     run_case("1184 x M=2048", [2048] * 1184)
