@@ -317,8 +317,9 @@ def run_ours(args, rank, world, local_rank):
                 kern[k]["gbps"] = algo[k] / (ms * 1e-3) / 1e9
         hbm_k = max((k for k in kern if k in ("aggregate", "project_count", "compact")), key=lambda k: kern[k]["ms"])
         traffic, traffic_src = None, None
-        try:        # DRAM bytes per launch of that kernel from the committed ncu capture of this same command
-            with open(os.path.join(ROOT, "profiles", "r01c_traffic.json")) as f:
+        try:        # DRAM bytes per launch of that kernel from the newest committed ncu capture of this same command
+            cands = sorted(fn for fn in os.listdir(os.path.join(ROOT, "profiles")) if fn.endswith("_traffic.json"))
+            with open(os.path.join(ROOT, "profiles", cands[-1])) as f:
                 tj = json.load(f)
             if tj.get("frames_per_launch") == args.batch:
                 traffic, traffic_src = tj["dram_bytes_per_launch"].get("k_" + hbm_k), tj["source"]
@@ -330,14 +331,20 @@ def run_ours(args, rank, world, local_rank):
         if "medoid" in timing:
             kern["medoid"]["pair_distances"] = pairs
             kern["medoid"]["gpairs_per_s"] = pairs / (timing["medoid"] * 1e-3) / 1e9
-            # FMA-pipe ceiling: 10 FP32-pipe lane-ops per pair distance (5 for the cdist chain,
-            # 4 for the correctly rounded sqrt, 1 to accumulate), 128 FP32 lanes per SM and clock
+            # XU-pipe ceiling: the screen pass needs one MUFU.SQRT per pair distance and the
+            # XU pipe retires 16 lanes per SM and clock; the exact passes (small instances, verified
+            # columns) are a rounding error next to it
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             mhz = clocks.get("sm_mhz") or 1965.0
-            ceil_gp = n_sm * 128 * mhz * 1e6 / 10.0 / 1e9
-            kern["medoid"]["bound"] = "fp32 FMA pipe (O(sum M^2) pair distances; reads only sum M points, L2-resident)"
+            ceil_gp = n_sm * 16 * mhz * 1e6 / 1e9
+            kern["medoid"]["bound"] = ("XU pipe: one MUFU.SQRT per pair distance in the screen pass (O(sum M^2) pair "
+                                       "distances; reads only sum M points, L2-resident)")
             kern["medoid"]["peak_gpairs_per_s"] = ceil_gp
             kern["medoid"]["frac"] = kern["medoid"]["gpairs_per_s"] / ceil_gp
+            if lifter.last_screen_stats is not None:
+                kern["medoid"]["screen_min_pts"] = lifter.screen_min_pts
+                kern["medoid"]["verified_columns_per_step"] = int(lifter.last_screen_stats.item())
+                kern["medoid"]["instances_per_step"] = int(m.size)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -357,7 +364,7 @@ def run_ours(args, rank, world, local_rank):
                          "achieved_gbps": sum(algo.values()) * world / (dev_ms / args.steps * 1e-3) / 1e9,
                          "frac_of_peak_per_gpu": sum(algo.values()) / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
                          "note": "sum of the kernels' algorithmic bytes over the whole step; the step is bound by the "
-                                 "medoid's FP32 dispatch, not by HBM (kernels.medoid)"},
+                                 "medoid's square roots (XU pipe), not by HBM (kernels.medoid)"},
             "kernels": kern,
             "gen_seconds": round(t_gen, 1),
         }

@@ -229,6 +229,28 @@ __device__ __forceinline__ uint32_t hmin3(const uint32_t *__restrict__ row, int 
     return c & ((c << 1) | (l >> 31)) & ((c >> 1) | (r << 31));
 }
 
+// Six consecutive words of one row around quad xw0: [xw0-1, xw0 .. xw0+3, xw0+4]; words outside the
+// row read as all ones, the row's last word gets ones above the image width (see hmin3).
+__device__ __forceinline__ void load_row6(const uint32_t *__restrict__ row, int xw0, int pitch, uint32_t tailmask,
+                                          bool vec, uint32_t (&w)[6])
+{
+    if (vec) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(row + xw0));
+        w[1] = c.x; w[2] = c.y; w[3] = c.z; w[4] = c.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[1 + k] = xw0 + k < pitch ? __ldg(row + xw0 + k) : 0xffffffffu;
+    }
+    w[0] = xw0 > 0 ? __ldg(row + xw0 - 1) : 0xffffffffu;
+    w[5] = xw0 + 4 < pitch ? __ldg(row + xw0 + 4) : 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        if (xw0 - 1 + k == pitch - 1) w[k] |= ~tailmask;
+}
+
+// cv2.erode(mask, ones(3,3)) on a bit plane, four consecutive words (one 16-byte store) per thread.
+// Planes whose pitch and offset are multiples of four words (every 1024-pixel-wide mask) take
+// 16-byte loads and stores; others go word by word through the same arithmetic.
 __global__ void __launch_bounds__(256)
 k_erode3x3(const uint32_t *__restrict__ bits_in, const int32_t *__restrict__ inst_desc,
            const int32_t *__restrict__ row_range, uint32_t *__restrict__ bits_out, int32_t *__restrict__ bbox)
@@ -236,38 +258,64 @@ k_erode3x3(const uint32_t *__restrict__ bits_in, const int32_t *__restrict__ ins
     const int i = blockIdx.y;
     const int32_t *d = inst_desc + i * CM3D_IN_WORDS;
     const int W = d[CM3D_IN_W], H = d[CM3D_IN_H], pitch = d[CM3D_IN_PITCH];
-    const int wd = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = wd < H * pitch;
-    uint32_t out = 0;
-    int y = 0, xw = 0;
+    const int64_t off = join64(d[CM3D_IN_BITS_LO], d[CM3D_IN_BITS_HI]);
+    const bool vec = ((pitch & 3) == 0) && ((off & 3) == 0);
+    const int quads_per_row = (pitch + 3) >> 2;
+    // the grid is sized for planes whose pitch is a multiple of four; others take more trips
+    for (int q0 = blockIdx.x * blockDim.x; q0 < H * quads_per_row; q0 += gridDim.x * blockDim.x) {
+    const int q = q0 + threadIdx.x;
+    const bool live = q < H * quads_per_row;
+    const int y = live ? q / quads_per_row : 0;
+    const int xw0 = live ? (q - y * quads_per_row) * 4 : 0;
+    uint32_t out[4] = {0u, 0u, 0u, 0u};
     if (live) {
-        y = wd / pitch;
-        xw = wd - y * pitch;
-        const int64_t off = join64(d[CM3D_IN_BITS_LO], d[CM3D_IN_BITS_HI]);
-        if (row_range && (y < row_range[2 * i] || y > row_range[2 * i + 1])) {
-            bits_out[off + wd] = 0u;            // no set pixel in this row: nothing survives, nothing to read
-            live = false;
+        const int r0 = row_range ? row_range[2 * i] : 0, r1 = row_range ? row_range[2 * i + 1] : H - 1;
+        if (y >= r0 && y <= r1) {          // a row without a set pixel: nothing survives, nothing to read
+            const uint32_t *plane = bits_in + off;
+            const uint32_t tailmask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xffffffffu;
+            uint32_t acc[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = y + dy;
+                // rows outside the image do not lower the minimum; rows outside the set range are all zero
+                if (yy < 0 || yy >= H) continue;
+                if (yy < r0 || yy > r1) { acc[0] = acc[1] = acc[2] = acc[3] = 0u; continue; }
+                uint32_t w[6];
+                load_row6(plane + (size_t)yy * pitch, xw0, pitch, tailmask, vec, w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t c = w[1 + k];
+                    acc[k] &= c & ((c << 1) | (w[k] >> 31)) & ((c >> 1) | (w[2 + k] << 31));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                out[k] = acc[k];
+                if (xw0 + k == pitch - 1) out[k] &= tailmask;
+                if (xw0 + k >= pitch) out[k] = 0u;
+            }
         }
-    }
-    if (live) {
-        const int64_t off = join64(d[CM3D_IN_BITS_LO], d[CM3D_IN_BITS_HI]);
-        const uint32_t *plane = bits_in + off;
-        const uint32_t tailmask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xffffffffu;
-        out = hmin3(plane + (size_t)y * pitch, xw, pitch, tailmask);
-        if (y > 0) out &= hmin3(plane + (size_t)(y - 1) * pitch, xw, pitch, tailmask);
-        if (y + 1 < H) out &= hmin3(plane + (size_t)(y + 1) * pitch, xw, pitch, tailmask);
-        if (xw == pitch - 1) out &= tailmask;
-        bits_out[off + wd] = out;
+        uint32_t *dst = bits_out + off + (size_t)y * pitch + xw0;
+        if (vec) {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (xw0 + k < pitch) dst[k] = out[k];
+        }
     }
     // bounding box of the surviving pixels: warp-reduce, then 4 atomics per warp at most
     int xmin = 0x7fffffff, ymin = 0x7fffffff, xmax = -1, ymax = -1;
-    if (out) {
-        xmin = xw * 32 + (__ffs(out) - 1);
-        xmax = xw * 32 + (31 - __clz(out));
-        ymin = ymax = y;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (out[k]) {
+            xmin = min(xmin, (xw0 + k) * 32 + (__ffs(out[k]) - 1));
+            xmax = max(xmax, (xw0 + k) * 32 + (31 - __clz(out[k])));
+            ymin = ymax = y;
+        }
     }
     const unsigned full = 0xffffffffu;
-    if (__any_sync(full, out != 0)) {
+    if (__any_sync(full, xmax >= 0)) {
         xmin = __reduce_min_sync(full, xmin);
         ymin = __reduce_min_sync(full, ymin);
         xmax = __reduce_max_sync(full, xmax);
@@ -278,6 +326,7 @@ k_erode3x3(const uint32_t *__restrict__ bits_in, const int32_t *__restrict__ ins
             atomicMax(&bbox[4 * i + 2], xmax);
             atomicMax(&bbox[4 * i + 3], ymax);
         }
+    }
     }
 }
 
@@ -336,7 +385,7 @@ extern "C" int cm3d_masks_erode3x3(const uint32_t *bits_in, const int32_t *inst_
     k_bbox_init<<<(n_inst + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bbox, n_inst);
     CM3D_LAUNCH_CHECK();
     if (max_words == 0) return CM3D_OK;
-    dim3 grid((max_words + 255) / 256, n_inst);
+    dim3 grid((max_words / 4 + 255) / 256 + 1, n_inst);      // four words per thread (the kernel loops if a plane needs more)
     k_erode3x3<<<grid, 256, 0, (cudaStream_t)stream>>>(bits_in, inst_desc, row_range, bits_out, bbox);
     CM3D_LAUNCH_CHECK();
     return CM3D_OK;

@@ -307,6 +307,61 @@ def test_screen_sqrt_error_exhaustive(lifter):
     assert 0 <= int(worst.item()) <= 2, int(worst.item())
 
 
+def test_erosion_odd_sizes_vs_cv2(lifter):
+    """cm3d_masks_pack_dense + cm3d_masks_erode3x3 against cv2.erode (the reference's call,
+    src/nuscenes/2d_to_3d.py:526-527) on widths whose pitch is not a multiple of four words and whose
+    planes start at unaligned word offsets (the scalar path of the four-words-per-thread kernel), next
+    to the aligned ones; eroded bits and bounding boxes must match exactly."""
+    import ctypes
+    import cv2
+    import torch
+    from cm3d_b200 import _native as N
+    rng = np.random.default_rng(5)
+    shapes = [(1, 1), (3, 2), (31, 7), (32, 9), (33, 5), (70, 40), (100, 33), (128, 64), (129, 17), (255, 50),
+              (1242, 60), (1024, 96), (96, 1024), (513, 3)]            # (W, H)
+    masks, descs, offs, word_off, byte_off = [], [], [], 0, 0
+    for W, H in shapes:
+        m = (rng.random((H, W)) < 0.93).astype(np.uint8)              # dense enough for the 3x3 minimum to keep pixels
+        m[rng.integers(0, H), :] = 0
+        if W > 40:
+            m[:, :3] = 1; m[:, -2:] = 1                               # set pixels on the borders: the +inf border rule
+        pitch = (W + 31) // 32
+        descs.append([word_off & 0xFFFFFFFF, word_off >> 32, W, H, pitch, 0, 0, len(masks)])
+        offs.append(byte_off)
+        masks.append(m)
+        word_off += pitch * H
+        byte_off += W * H
+    desc = np.array(descs, np.int64).astype(np.int32)
+    dev = "cuda:0"
+    d_masks = torch.from_numpy(np.concatenate([m.reshape(-1) for m in masks])).to(dev)
+    d_off = torch.from_numpy(np.array(offs, np.int64)).to(dev)
+    d_desc = torch.from_numpy(desc.reshape(-1)).to(dev)
+    max_words = max(d[4] * d[3] for d in descs)
+    raw = torch.zeros(word_off + 4, dtype=torch.int32, device=dev)
+    out = torch.full((word_off + 4,), -1, dtype=torch.int32, device=dev)
+    bbox = torch.zeros(4 * len(shapes), dtype=torch.int32, device=dev)
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    N.call("cm3d_masks_pack_dense", p(d_masks), p(d_off), p(d_desc), len(shapes), int(max_words), p(raw), st)
+    N.call("cm3d_masks_erode3x3", p(raw), p(d_desc), None, len(shapes), int(max_words), p(out), p(bbox), st)
+    torch.cuda.synchronize()
+    out, bbox = out.cpu().numpy().view(np.uint32), bbox.cpu().numpy().reshape(-1, 4)
+    for k, ((W, H), m) in enumerate(zip(shapes, masks)):
+        want = cv2.erode(m, np.ones((3, 3), np.uint8))
+        pitch = descs[k][4]
+        w0 = descs[k][0]
+        words = out[w0:w0 + pitch * H].reshape(H, pitch)
+        got = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(H, pitch * 32).astype(np.uint8)
+        assert np.array_equal(got[:, :W], want), (W, H)
+        assert not got[:, W:].any(), (W, H)
+        ys, xs = np.nonzero(want)
+        if ys.size:
+            assert bbox[k].tolist() == [xs.min(), ys.min(), xs.max(), ys.max()], (W, H)
+        else:
+            assert bbox[k, 2] < 0 and bbox[k, 3] < 0
+    assert out[word_off] == 0xFFFFFFFF                               # nothing written past the last plane
+
+
 def test_fast_sqrt_exhaustive(lifter):
     """The medoid kernel's branch-free sqrt equals IEEE sqrt.rn on every float of its domain."""
     import ctypes
@@ -458,6 +513,18 @@ def test_full_size_configs(lifter, cfg):
         got = sums[r.seg_offsets[i]:r.seg_offsets[i + 1]]
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (cfg, i, idx.size)
         assert r.medoid_local[i] == j or f.dataset == "kitti" and idx.size < 4
+    # the production path (screen + verify, no column sums) returns the same medoids, and with the
+    # screen forced down to 32-point instances as well
+    for thr in (lifter.screen_min_pts, 32):
+        keep, lifter.screen_min_pts = lifter.screen_min_pts, thr
+        try:
+            r2 = lifter.lift_frames([f], with_points=False)[0]
+        finally:
+            lifter.screen_min_pts = keep
+        assert int(lifter.last_screen_stats.item()) >= sum(1 for m in sizes if m >= max(thr, 32))
+        assert np.array_equal(r2.medoid_local, r.medoid_local), (cfg, thr)
+        assert np.array_equal(r2.medoid_point_idx, r.medoid_point_idx)
+        assert np.array_equal(r2.centroids.view(np.uint32), r.centroids.view(np.uint32))
 
 
 def _check_vs_c_oracle(f, r):
