@@ -428,19 +428,27 @@ __device__ __forceinline__ uint32_t hit_insert(uint32_t hw, uint32_t id)
     return out;
 }
 
-// K2 (count pass): one block per tile of the aggregated cloud, 4 consecutive slots per thread.
-// Per vcam: (1) every point is tested against the vcam's five conservative cull planes (3 FMAs +
-// a compare each, early exit; points are in firing order, so whole warps drop out together);
-// (2) warps with a survivor run the exact chain; in-image points append (pixel, slot) to a
-// per-vcam list in shared memory; (3) the list is walked by ALL threads of the block (instance
-// lookup grid -> bbox -> one bit probe), so the walk is load balanced instead of divergent.
-// Hit words are kept in shared memory during the walk (a slot is touched by one thread per vcam
+// K2 (count pass): one block per tile of the aggregated cloud, 4 consecutive slots per thread, and
+// every WARP on its own: a warp owns 128 consecutive slots (points in firing order: one narrow
+// azimuth wedge), its own in-image list and its own hit words, so there is no block barrier between
+// cameras and a warp that does not see a camera moves on while another one walks its masks.
+// Per vcam: (1) every point is tested against the vcam's five conservative cull planes (3 FMAs + a
+// compare each, early exit; whole warps drop a camera together); (2) threads that still hold a
+// candidate run the exact chain; in-image points are compacted (ballots, no atomics) into the
+// warp's list; (3) the list is walked by all 32 lanes (instance lookup grid -> one bit probe per
+// candidate), so the walk is load balanced instead of divergent.
+// Hit words are kept in shared memory during the walk (a slot is touched by one lane per vcam
 // pass) and leave with one 16-byte store per thread.
+constexpr int kWarpSlots = kTile / (kBlock / 32);      // slots (and list entries) per warp
+
 template <int SIG>
 __device__ __forceinline__ void project_count_tile(FrameTables &ft, int *s_hist, uint32_t *s_hw, int32_t *s_lcode,
-                                                   uint16_t *s_lslot, int *s_ln, const float *__restrict__ xyzw,
+                                                   uint16_t *s_lslot, const float *__restrict__ xyzw,
                                                    int64_t n_slots, int64_t base, int cnt, int32_t *__restrict__ pix)
 {
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    int32_t *wl_code = s_lcode + warp * kWarpSlots;
+    uint16_t *wl_slot = s_lslot + warp * kWarpSlots;
     const int s0 = threadIdx.x * 4;
     const int np = max(0, min(4, cnt - s0));
     float xs[4] = {0.f, 0.f, 0.f, 0.f}, ys[4] = {0.f, 0.f, 0.f, 0.f}, zs[4] = {0.f, 0.f, 0.f, 0.f};
@@ -459,6 +467,7 @@ __device__ __forceinline__ void project_count_tile(FrameTables &ft, int *s_hist,
         nmg[k] = -((fabsf(qx[k]) + fabsf(qy[k])) + fabsf(qz[k])) * 0x1p-17f;     // -S * 2^-17
     }
     *reinterpret_cast<uint4 *>(s_hw + s0) = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
 
     for (int v = 0; v < ft.n_vcams; ++v) {
         const VcamS &vc = ft.vcam[v];
@@ -476,20 +485,27 @@ __device__ __forceinline__ void project_count_tile(FrameTables &ft, int *s_hist,
             }
         }
         int32_t code[4] = {-1, -1, -1, -1};
-        // (2) exact chain for warps that still hold a candidate
-        if (cand != 0) {
-            project_sig<SIG, 4>(vc, ft.min_depth, xs, ys, zs, code);
-            int n_in = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!((cand >> k) & 1u)) code[k] = -1;       // k >= np, or culled (then it is -1 anyway)
-                n_in += code[k] >= 0;
-            }
-            if (n_in) {
-                int at = atomicAdd(s_ln + v, n_in);
+        int n_list = 0;
+        if (__any_sync(0xffffffffu, cand != 0)) {
+            // (2) exact chain for the threads that still hold a candidate
+            if (cand != 0) {
+                project_sig<SIG, 4>(vc, ft.min_depth, xs, ys, zs, code);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (code[k] >= 0) { s_lcode[at] = code[k]; s_lslot[at] = (uint16_t)(s0 + k); ++at; }
+                    if (!((cand >> k) & 1u)) code[k] = -1;       // k >= np, or culled (then it is -1 anyway)
+            }
+            // in-image points -> the warp's list, in slot order; pixel column / row 0 is never a member
+            // (the reference's `logical_and(floored_points, ...)` quirk)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool in = code[k] >= 0 && (code[k] & 0xffff) != 0 && (code[k] >> 16) != 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const int at = n_list + __popc(bal & lanemask_lt());
+                    wl_code[at] = code[k];
+                    wl_slot[at] = (uint16_t)(s0 + k);
+                }
+                n_list += __popc(bal);
             }
         }
         if (pix) {
@@ -497,13 +513,12 @@ __device__ __forceinline__ void project_count_tile(FrameTables &ft, int *s_hist,
             for (int k = 0; k < 4; ++k)
                 if (k < np) pix[(int64_t)v * n_slots + base + s0 + k] = code[k];
         }
-        __syncthreads();
-        // (3) walk the in-image list of this vcam
-        const int n_list = s_ln[v];
-        for (int e = threadIdx.x; e < n_list; e += blockDim.x) {
-            const int32_t code = s_lcode[e];
+        if (n_list == 0) continue;             // uniform over the warp
+        __syncwarp();
+        // (3) walk the warp's in-image list of this vcam
+        for (int e = lane; e < n_list; e += 32) {
+            const int32_t code = wl_code[e];
             const int fx = code & 0xffff, fy = code >> 16;
-            if (fx == 0 || fy == 0) continue;                 // `logical_and(floored_points, ...)` quirk
             const uint32_t *cell = vc.grid + (size_t)((fy / CM3D_CELL) * vc.grid_nx + fx / CM3D_CELL) * vc.grid_nwords;
             const uint32_t bit = 1u << (fx & 31);
             uint32_t h = 0;
@@ -515,15 +530,15 @@ __device__ __forceinline__ void project_count_tile(FrameTables &ft, int *s_hist,
                     c &= c - 1u;
                     const InstS &si = ft.inst[j];
                     if (__ldg(si.plane + (size_t)fy * si.pitch + (fx >> 5)) & bit) {
-                        if (!touched) { h = s_hw[s_lslot[e]]; touched = true; }
+                        if (!touched) { h = s_hw[wl_slot[e]]; touched = true; }
                         h = (h >> 24) ? (h | 0xff000000u) : ((h << 8) | (uint32_t)(j + 1));   // append, newest in byte 0
                         atomicAdd(&s_hist[j], 1);
                     }
                 }
             }
-            if (touched) s_hw[s_lslot[e]] = h;
+            if (touched) s_hw[wl_slot[e]] = h;
         }
-        __syncthreads();                       // the list buffers are reused by the next vcam
+        __syncwarp();                          // the list is reused by the next vcam
     }
 }
 
@@ -541,23 +556,21 @@ k_project_count(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *
     __shared__ __align__(16) uint32_t s_hw[kTile];
     __shared__ int32_t s_lcode[kTile];
     __shared__ uint16_t s_lslot[kTile];
-    __shared__ int s_ln[CM3D_MAX_VCAMS];     // in-image list length, one counter per vcam pass
 
     const int t = blockIdx.x;
     const int f = sweep_desc[(size_t)tile_sweep[t] * CM3D_SW_WORDS + CM3D_SW_FRAME];
     const int32_t *fd = frame_desc + (size_t)f * CM3D_FR_WORDS;
     load_frame_tables(ft, fd, vcam_desc, cam_inst_list, inst_desc, inst_bbox, chains, bits, vcam_grid);
     for (int j = threadIdx.x; j < CM3D_MAX_INST + 2; j += blockDim.x) s_hist[j] = 0;
-    if (threadIdx.x < CM3D_MAX_VCAMS) s_ln[threadIdx.x] = 0;
     __syncthreads();
 
     const int cnt = tile_cnt[t];
     const int64_t base = (int64_t)t * kTile;
     switch (ft.chain_sig) {
-    case kSigTRTR: project_count_tile<kSigTRTR>(ft, s_hist, s_hw, s_lcode, s_lslot, s_ln, xyzw, n_slots, base, cnt, pix); break;
-    case kSigTR:   project_count_tile<kSigTR>(ft, s_hist, s_hw, s_lcode, s_lslot, s_ln, xyzw, n_slots, base, cnt, pix); break;
-    case kSigAAR:  project_count_tile<kSigAAR>(ft, s_hist, s_hw, s_lcode, s_lslot, s_ln, xyzw, n_slots, base, cnt, pix); break;
-    default:       project_count_tile<kSigGeneric>(ft, s_hist, s_hw, s_lcode, s_lslot, s_ln, xyzw, n_slots, base, cnt, pix); break;
+    case kSigTRTR: project_count_tile<kSigTRTR>(ft, s_hist, s_hw, s_lcode, s_lslot, xyzw, n_slots, base, cnt, pix); break;
+    case kSigTR:   project_count_tile<kSigTR>(ft, s_hist, s_hw, s_lcode, s_lslot, xyzw, n_slots, base, cnt, pix); break;
+    case kSigAAR:  project_count_tile<kSigAAR>(ft, s_hist, s_hw, s_lcode, s_lslot, xyzw, n_slots, base, cnt, pix); break;
+    default:       project_count_tile<kSigGeneric>(ft, s_hist, s_hw, s_lcode, s_lslot, xyzw, n_slots, base, cnt, pix); break;
     }
     __syncthreads();
     const int s0 = threadIdx.x * 4;
