@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 7
+#define CM3D_ABI_VERSION 8
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
@@ -195,22 +195,24 @@ int cm3d_compact_segments(const float *xyzw, const int32_t *tile_cnt, const int3
  * it must be >= item_off[n_inst_total] (seg_cap/CM3D_MEDOID_COLS + 2*n_inst_total always is).
  * item_off / item_inst: the schedule written by cm3d_scan_segments.
  *
- * Screen + verify (same result, ~1.7x less work; csrc/medoid.cu has the error bound): with
- * screen_sums (seg_cap floats), screen_min (n_inst_total words) and screen_min_pts > 0 given and
+ * Screen + verify (same result, ~3x less work; csrc/medoid.cu has the error bounds): with
+ * screen_sums (seg_cap floats), screen_min (2 * n_inst_total words) and screen_min_pts > 0 given and
  * col_sums NULL, instances with screen_min_pts <= M <= 2^19 points get approximate column sums
  * first (bit-identical squared distances, MUFU square root, flat accumulation) and only the
  * columns within the proven error bound of the approximate minimum are summed exactly, in the
- * reference's order; the argmin runs over those.  Smaller instances, instances with coordinates
- * outside [2^-20, 2^60] and every call with col_sums take the all-exact path.
- * screen_stats (optional, 1 word, zeroed by the caller): receives the number of verified columns.
- * item_pos (optional scratch, max_items words): item -> schedule position table, so that the
- * blocks of the three item-grid launches find their instance with one load instead of a search. */
+ * reference's order; the argmin runs over those.  Instances whose squared norms share one binade
+ * (nuScenes' global frame) have an exactly symmetric squared-distance matrix and are screened over
+ * the pairs i <= j only (screen_flags bit 0 turns that off).  Smaller instances, instances with
+ * coordinates outside the fast square root's range and every call with col_sums take the all-exact
+ * path.  screen_stats (optional, 1 word, zeroed by the caller): receives the number of verified
+ * columns.  item_pos (optional scratch, max_items words): item -> schedule position table, so that
+ * the blocks of the item-grid launches find their instance with one load instead of a search. */
 int cm3d_medoid(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off,
                 const int32_t *seg_point_idx, const int32_t *item_off, const int32_t *item_inst,
                 int n_inst_total,
                 int max_items, unsigned long long *medoid_best, float *col_sums,
-                float *screen_sums, uint32_t *screen_min, int screen_min_pts, int32_t *screen_stats,
-                int32_t *item_pos, int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
+                float *screen_sums, uint32_t *screen_min, int screen_min_pts, int screen_flags,
+                int32_t *screen_stats, int32_t *item_pos, int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
                 const int32_t *errflags, void *stream);
 #define CM3D_SCREEN_MIN_PTS 512   /* default screen_min_pts */
 

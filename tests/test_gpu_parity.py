@@ -178,7 +178,7 @@ def test_small_segments_all_sizes(lifter):
     p = lambda x: ctypes.c_void_p(x.data_ptr())
     d_inst = torch.arange(n, dtype=torch.int32, device=dev)
     N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), p(d_inst), n, int(item_off[-1]) + 3, p(best), p(col),
-           None, None, 0, None, None,
+           None, None, 0, 0, None, None,
            p(ml), p(mp), p(cen), p(err), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     col, ml = col.cpu().numpy(), ml.cpu().numpy()
@@ -189,7 +189,7 @@ def test_small_segments_all_sizes(lifter):
         assert ml[k] == j, m
 
 
-def _medoid_abi(pts_list, screen_min_pts, want_sums=False):
+def _medoid_abi(pts_list, screen_min_pts, want_sums=False, screen_flags=0):
     """cm3d_medoid on hand-made segments (list of (3,M) fp32) through the C ABI.
     Returns (medoid_local, column sums or None, verified-column count)."""
     import torch, ctypes
@@ -209,7 +209,7 @@ def _medoid_abi(pts_list, screen_min_pts, want_sums=False):
     best = torch.full((n,), -1, dtype=torch.int64, device=dev)
     col = torch.zeros(cap, dtype=torch.float32, device=dev) if want_sums else None
     ssum = torch.zeros(cap, dtype=torch.float32, device=dev)
-    smin = torch.zeros(n, dtype=torch.int32, device=dev)
+    smin = torch.zeros(2 * n, dtype=torch.int32, device=dev)
     stats = torch.zeros(1, dtype=torch.int32, device=dev)
     ipos = torch.zeros(int(item_off[-1]) + 3, dtype=torch.int32, device=dev) if screen_min_pts != 32 else None
     ml = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -219,7 +219,7 @@ def _medoid_abi(pts_list, screen_min_pts, want_sums=False):
     p = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None else None
     d_inst = torch.arange(n, dtype=torch.int32, device=dev)
     N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), p(d_inst), n, int(item_off[-1]) + 3, p(best), p(col),
-           p(ssum), p(smin), int(screen_min_pts), p(stats), p(ipos),
+           p(ssum), p(smin), int(screen_min_pts), int(screen_flags), p(stats), p(ipos),
            p(ml), p(mp), p(cen), p(err), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     sums = None
@@ -238,6 +238,11 @@ def _screen_cases():
               1039, 1040, 1041, 1279, 1280, 1281, 2047, 2048, 2077, 4095, 4096, 4097, 4111, 4112, 4113, 4351,
               4352, 4353, 5000, 8191, 8192, 8193, 8208, 12289]:
         cases.append((rng.normal(0, 3, (3, m)) + ctr).astype(np.float32))
+    # squared norms across a binade boundary (|p|^2 ~ 2^21 at (1024, 1024, 0)): NOT symmetric-eligible;
+    # just inside a binade on either side of it: eligible
+    for c in ((1024.0, 1024.0, 0.0), (1024.0, 1030.0, 0.0), (1020.0, 1022.0, 0.0)):
+        for m in (700, 2600):
+            cases.append((rng.normal(0, 1.5, (3, m)) + np.array(c)[:, None]).astype(np.float32))
     # local-frame coordinates (KITTI / Waymo magnitude): little cancellation noise
     for m in [100, 777, 3000, 4100]:
         cases.append(rng.normal(0, 2, (3, m)).astype(np.float32) + np.float32(10.0))
@@ -280,9 +285,9 @@ def test_medoid_screen_equals_exact(lifter):
     for k in list(range(0, len(cases), 5)) + list(range(len(cases) - 12, len(cases))):
         j, ref = CO.medoid(cases[k], want_sums=True)
         assert np.array_equal(sums[k].view(np.uint32), ref.view(np.uint32)) and exact[k] == j
-    for thr in (32, 512):
-        got, _, verified = _medoid_abi(cases, thr)
-        assert np.array_equal(got, exact), (thr, np.nonzero(got != exact)[0])
+    for thr, flags in ((32, 0), (512, 0), (32, 1), (512, 1)):        # flags 1: symmetric screen off
+        got, _, verified = _medoid_abi(cases, thr, screen_flags=flags)
+        assert np.array_equal(got, exact), (thr, flags, np.nonzero(got != exact)[0])
         assert verified >= sum(1 for c in cases if c.shape[1] >= thr) - 1     # the out-of-range instance is not screened
     # random segments: the screen leaves about one candidate per instance
     rng = np.random.default_rng(11)
