@@ -341,16 +341,29 @@ def run_ours(args, rank, world, local_rank):
         if "medoid" in timing:
             kern["medoid"]["pair_distances"] = pairs
             kern["medoid"]["gpairs_per_s"] = pairs / (timing["medoid"] * 1e-3) / 1e9
-            # XU-pipe ceiling: the screen pass needs one MUFU.SQRT per pair distance and the
-            # XU pipe retires 16 lanes per SM and clock; the exact passes (small instances, verified
-            # columns) are a rounding error next to it
+            # XU-pipe ceiling: one MUFU square root per EVALUATED pair and the XU pipe retires
+            # 16 lanes per SM and clock.  Instances whose squared-distance matrix is exactly symmetric
+            # (mode 2) are screened over the pairs i <= j of 256-column strips: about half the roots.
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             mhz = clocks.get("sm_mhz") or 1965.0
-            ceil_gp = n_sm * 16 * mhz * 1e6 / 1e9
-            kern["medoid"]["bound"] = ("XU pipe: one MUFU.SQRT per pair distance in the screen pass (O(sum M^2) pair "
-                                       "distances; reads only sum M points, L2-resident)")
-            kern["medoid"]["peak_gpairs_per_s"] = ceil_gp
-            kern["medoid"]["frac"] = kern["medoid"]["gpairs_per_s"] / ceil_gp
+            ceil_roots = n_sm * 16 * mhz * 1e6 / 1e9
+            roots = pairs
+            if lifter.last_screen_modes is not None:
+                modes = lifter.last_screen_modes.cpu().numpy()
+                mm = m.astype(np.float64)
+                T = np.ceil(mm / 256.0)
+                full_blocks = np.floor(mm / 256.0)
+                # strips J = 0..T-1: rows [0, min(m, 256 (J+1))) x cols of the strip
+                tri = 256.0 * 256.0 * full_blocks * (full_blocks + 1) / 2.0 + (mm - 256.0 * full_blocks) * mm
+                roots = float(np.where(modes == 2, tri, mm * mm).sum())
+                kern["medoid"]["instances_by_mode"] = {"exact": int((modes == 0).sum()), "screen_all_pairs": int((modes == 1).sum()),
+                                                       "screen_symmetric": int((modes == 2).sum())}
+            kern["medoid"]["bound"] = ("XU pipe: one MUFU.SQRT per evaluated pair distance in the screen pass (reads only "
+                                       "sum M points, L2-resident); symmetric instances evaluate the pairs i <= j only")
+            kern["medoid"]["square_roots"] = roots
+            kern["medoid"]["groots_per_s"] = roots / (timing["medoid"] * 1e-3) / 1e9
+            kern["medoid"]["peak_groots_per_s"] = ceil_roots
+            kern["medoid"]["frac"] = kern["medoid"]["groots_per_s"] / ceil_roots
             if lifter.last_screen_stats is not None:
                 kern["medoid"]["screen_min_pts"] = lifter.screen_min_pts
                 kern["medoid"]["verified_columns_per_step"] = int(lifter.last_screen_stats.item())

@@ -152,6 +152,7 @@ class Lifter:
         self.screen_min_pts = SCREEN_MIN_PTS   # medoid: instances this large are screened, then verified; 0 = all exact
         self.screen_flags = 0                  # bit 0: no symmetric screen (every screened instance does all M^2 pairs)
         self.last_screen_stats = None          # device int32[1]: columns the last run() verified exactly
+        self.last_screen_modes = None          # device int32[I]: 0 exact, 1 screened (all pairs), 2 screened (pairs i <= j)
         self.timing = None          # dict label -> [(start_event, end_event)] when bench.py profiles
 
     def _call(self, label: str, name: str, *args):
@@ -308,7 +309,7 @@ class Lifter:
 
         # ---- medoid (screen + verify for instances of >= screen_min_pts points, see csrc/medoid.cu)
         col_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if want_col_sums else None
-        screen_stats = None
+        screen_stats = screen_min = None
         if do_medoid and I:
             max_items = seg_cap // MEDOID_COLS + 2 * I
             screen = self.screen_min_pts > 0 and not want_col_sums
@@ -323,6 +324,7 @@ class Lifter:
                    _ptr(o("medoid_local")), _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
             self.launches += (6 if self.screen_flags & 1 else 9) if screen else 3
         self.last_screen_stats = screen_stats
+        self.last_screen_modes = screen_min[I:] if (do_medoid and I and screen_min is not None) else None
         # ---- KITTI: principal-axes box + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479)
         obb = None
         if want_obb is None:
