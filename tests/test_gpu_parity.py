@@ -243,6 +243,14 @@ def _screen_cases():
     for c in ((1024.0, 1024.0, 0.0), (1024.0, 1030.0, 0.0), (1020.0, 1022.0, 0.0)):
         for m in (700, 2600):
             cases.append((rng.normal(0, 1.5, (3, m)) + np.array(c)[:, None]).astype(np.float32))
+    # sensor-frame instances that ARE symmetric-eligible (one binade of |p|^2, small extent), at several magnitudes
+    for c, sg in (((35.0, 2.0, 15.0), 0.5), ((6.0, -1.0, 5.5), 0.15), ((-60.0, 20.0, 1.0), 0.8), ((0.9, 0.1, 0.2), 0.02)):
+        for m in (600, 3100):
+            cases.append((rng.normal(0, sg, (3, m)) + np.array(c)[:, None]).astype(np.float32))
+    # squared norms hugging the top of a binade (the margin rule) and the D^2 <= min(n)/4 rule
+    top = np.sqrt(2.0 ** 21) / np.sqrt(2.0)
+    cases.append((rng.normal(0, 0.003, (3, 900)) * np.array([[1.0], [1.0], [0.0]]) + np.array([[top - 0.004], [top - 0.004], [0.0]])).astype(np.float32))
+    cases.append((rng.uniform(-1, 1, (3, 1500)) * 2.4 + np.array([[5.0], [5.0], [5.0]])).astype(np.float32))
     # local-frame coordinates (KITTI / Waymo magnitude): little cancellation noise
     for m in [100, 777, 3000, 4100]:
         cases.append(rng.normal(0, 2, (3, m)).astype(np.float32) + np.float32(10.0))
