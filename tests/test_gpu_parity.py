@@ -226,6 +226,7 @@ def _medoid_abi(pts_list, screen_min_pts, want_sums=False, screen_flags=0):
     if want_sums:
         c = col.cpu().numpy()
         sums = [c[seg_off[k]:seg_off[k + 1]] for k in range(n)]
+    _medoid_abi.last_modes = smin.cpu().numpy()[n:]            # 0 exact, 1 screened (all pairs), 2 screened (pairs i <= j)
     return ml.cpu().numpy(), sums, int(stats.item())
 
 
@@ -297,6 +298,21 @@ def test_medoid_screen_equals_exact(lifter):
         got, _, verified = _medoid_abi(cases, thr, screen_flags=flags)
         assert np.array_equal(got, exact), (thr, flags, np.nonzero(got != exact)[0])
         assert verified >= sum(1 for c in cases if c.shape[1] >= thr) - 1     # the out-of-range instance is not screened
+        modes = _medoid_abi.last_modes
+        n2 = [float(np.sum(c.astype(np.float64) ** 2, 0).min()) for c in cases]
+        for k, c in enumerate(cases):
+            if c.shape[1] < thr:
+                assert modes[k] == 0
+            elif flags & 1:
+                assert modes[k] in (0, 1)
+        if flags == 0:
+            # global-frame clouds around (1200, 950, 1) sit inside one binade of |p|^2: symmetric screen;
+            # the ones centred on (1024, 1024, 0) straddle 2^21: all-pairs screen
+            g = [k for k, c in enumerate(cases) if c.shape[1] >= 512 and abs(c[0].mean() - 1200) < 1 and abs(c[1].mean() - 950) < 1]
+            assert len(g) >= 20 and all(modes[k] == 2 for k in g)
+            st = [k for k, c in enumerate(cases) if c.shape[1] >= 700 and c[0].std() > 1.0 and abs(c[0].mean() - 1024) < 0.5 and abs(c[1].mean() - 1024) < 0.5]
+            assert len(st) == 2 and all(modes[k] == 1 for k in st)
+            assert (modes == 2).sum() >= 30
     # random segments: the screen leaves about one candidate per instance
     rng = np.random.default_rng(11)
     rnd = [(rng.normal(0, 2, (3, int(m))) + np.array([[900.0], [1500.0], [2.0]])).astype(np.float32)
