@@ -300,6 +300,18 @@ def run_ours(args, rank, world, local_rank):
     d2h_bytes = sum(int(lifter._out_layout(p.n_frames, p.n_inst)["_words"]) * 4 for p in subs)
     h2d_bytes = sum(p.h2d_bytes for p in subs)
 
+    # ---- the same frames as FrameSpecs (what the drop-in scripts hand over): host packing included
+    fs_fps = None
+    if world == 1 and not args.no_framespec_leg:
+        for _ in lifter.lift_frame_stream(iter(frames), batch_frames=args.batch):
+            pass
+        t0 = time.perf_counter()
+        n_fs = 0
+        for res in lifter.lift_frame_stream(iter(frames * 2), batch_frames=args.batch):
+            n_fs += len(res)
+        torch.cuda.synchronize()
+        fs_fps = n_fs / (time.perf_counter() - t0)
+
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -383,6 +395,10 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_gbps_rank0": round(h2d_gbps, 1), "sub_batch_frames": sub,
                     "api": "Lifter.lift_packed_stream (pinned host buffers in, label block out)"},
             "gpu_launches": launches,
+            "e2e_from_framespecs": None if fs_fps is None else {
+                "value": fs_fps, "unit": UNIT,
+                "note": "Lifter.lift_frame_stream over 2 x the step's FrameSpecs (numpy sweeps + RLE masks + calibration): "
+                        "pack_frames on one worker thread (Python + numpy, ~5 ms per frame) bounds it, not the GPU"},
             "roofline": roof,
             "path_hbm": {"algorithmic_bytes_per_step": int(sum(algo.values())) * world,
                          "achieved_gbps": sum(algo.values()) * world / (dev_ms / args.steps * 1e-3) / 1e9,
@@ -429,6 +445,7 @@ def main():
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame-parallel", action="store_true", help="skip the one-process-per-core CPU baseline")
+    ap.add_argument("--no-framespec-leg", action="store_true", help="skip the FrameSpec-level (host packing included) leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
