@@ -40,23 +40,27 @@ def _f32_bits(x) -> int:
     return int(np.float32(x).view(np.int32))
 
 
+_I3 = np.eye(3)
+_OFF_PLANES = np.tile(np.array([0.0, 0.0, 0.0, 1.0], np.float32), (5, 1))
+
+
 def _compose(ops):
     """fp64 composition of a transform chain: p_out = M p + c; also sum of |translations|_1 after
     the first op and whether every linear part is orthogonal to 1e-3."""
-    M, c, tau, ok = np.eye(3), np.zeros(3), 0.0, True
+    M, c, tau, ok = _I3, np.zeros(3), 0.0, True
     for k, (kind, m) in enumerate(ops):
         m = np.asarray(m, np.float64)
         if kind == "T":
             c = c + m
             if k:
-                tau += np.abs(m).sum()
+                tau += abs(float(m[0])) + abs(float(m[1])) + abs(float(m[2]))
         else:
             L = m if kind == "R" else m[:, :3]
-            ok &= bool(np.abs(L @ L.T - np.eye(3)).max() < 1e-3)
+            ok = ok and bool(np.abs(L @ L.T - _I3).max() < 1e-3)
             M, c = L @ M, L @ c
             if kind == "A":
                 c = c + m[:, 3]
-                tau += np.abs(m[:, 3]).sum()
+                tau += abs(float(m[0, 3])) + abs(float(m[1, 3])) + abs(float(m[2, 3]))
     return M, c, tau, ok
 
 
@@ -65,32 +69,35 @@ def cull_planes(cam, W: int, H: int, min_dist32, tref):
     CM3D_VC_PLANES).  Error budget (u = 2^-24, S = |q|_1, tau = |translations|_1): the reference's
     fp32 chain is within 96u(S+tau) of the exact composition per coordinate, its pixel numerators
     within 4u of theirs, and evaluating a plane scaled to |n|_1 <= 1 in fp32 costs <= 6uS + 4u|d|;
-    all of it is below S*2^-17 + mg0, and mg0 is folded into d.  Returns (planes[5,4] f32, flags)."""
-    off = np.tile(np.array([0.0, 0.0, 0.0, 1.0], np.float32), (5, 1))
+    all of it is below S*2^-17 + mg0, and mg0 is folded into d.  Returns (planes[5,4] f32, flags).
+    (The five planes are evaluated as one 5x3 product: this runs once per camera and frame on the host.)"""
     K = np.asarray(cam.K, np.float64)
-    simple = bool(K[0, 1] == 0 and K[1, 0] == 0 and K[0, 0] != 0 and K[1, 1] != 0 and
-                  K[2, 0] == 0 and K[2, 1] == 0 and K[2, 2] == 1)
+    k00, k01, k02 = float(K[0, 0]), float(K[0, 1]), float(K[0, 2])
+    k10, k11, k12 = float(K[1, 0]), float(K[1, 1]), float(K[1, 2])
+    bottom_ok = K[2, 0] == 0 and K[2, 1] == 0 and K[2, 2] == 1
+    simple = bool(k01 == 0 and k10 == 0 and k00 != 0 and k11 != 0 and bottom_ok)
     flags = 1 if simple else 0
     M, c, tau, ok = _compose(cam.ops)
-    if not ok or not (K[2, 0] == 0 and K[2, 1] == 0 and K[2, 2] == 1) or not np.all(np.isfinite(M)):
-        return off, flags
+    if not ok or not bottom_ok or not np.all(np.isfinite(M)):
+        return _OFF_PLANES.copy(), flags
     tref = np.asarray(tref, np.float64)
     first_T = len(cam.ops) and cam.ops[0][0] == "T"
-    tau += np.abs(tref + np.asarray(cam.ops[0][1], np.float64)).sum() if first_T else np.abs(tref).sum()
+    t0 = tref + np.asarray(cam.ops[0][1], np.float64) if first_T else tref
+    tau += abs(float(t0[0])) + abs(float(t0[1])) + abs(float(t0[2]))
     c2 = c - M @ tref                                   # p = q - tref
-    cam_planes = [((0.0, 0.0, 1.0), -float(min_dist32)),                     # z > min_dist
-                  (tuple(K[0]), 0.0), ((-K[0, 0], -K[0, 1], W - K[0, 2]), 0.0),   # 0 < r0, r0 < W z
-                  (tuple(K[1]), 0.0), ((-K[1, 0], -K[1, 1], H - K[1, 2]), 0.0)]   # 0 < r1, r1 < H z
-    out = np.zeros((5, 4), np.float64)
-    for k, (abc, d0) in enumerate(cam_planes):
-        abc = np.asarray(abc, np.float64)
-        kappa = 1.75 * np.abs(abc).sum()
-        n = abc @ M / kappa
+    abc = np.array([[0.0, 0.0, 1.0],                                  # z > min_dist
+                    [k00, k01, k02], [-k00, -k01, W - k02],           # 0 < r0, r0 < W z
+                    [k10, k11, k12], [-k10, -k11, H - k12]])          # 0 < r1, r1 < H z
+    d0 = np.array([-float(min_dist32), 0.0, 0.0, 0.0, 0.0])
+    kappa = 1.75 * np.abs(abc).sum(1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        n = (abc @ M) / kappa[:, None]
         d = (abc @ c2 + d0) / kappa
-        if not (np.abs(n).sum() <= 1.0) or not np.isfinite(d):
-            return off, flags
-        out[k, :3], out[k, 3] = n, d
-    mg0 = 2.0 ** -17 * tau + 2.0 ** -20 * np.abs(out[:, 3]).max() + 1e-30
+    if not bool((np.abs(n).sum(1) <= 1.0).all()) or not bool(np.isfinite(d).all()):
+        return _OFF_PLANES.copy(), flags
+    out = np.empty((5, 4), np.float64)
+    out[:, :3], out[:, 3] = n, d
+    mg0 = 2.0 ** -17 * tau + 2.0 ** -20 * float(np.abs(d).max()) + 1e-30
     out[:, 3] += mg0
     out32 = out.astype(np.float32)
     out32[:, 3] = np.nextafter(out32[:, 3], np.float32(np.inf))   # rounding of d never tightens a plane
