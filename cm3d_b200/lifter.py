@@ -372,7 +372,8 @@ class Lifter:
         return res
 
     @_on_device
-    def lift_frame_stream(self, frames, batch_frames: int = 32, timer: Optional[dict] = None, depth: int = 2):
+    def lift_frame_stream(self, frames, batch_frames: int = 32, timer: Optional[dict] = None, depth: int = 2,
+                          pack_workers: int = 1):
         """Drop-in scripts' entry: an iterator of FrameSpecs in, lists of LiftResult (one list per
         batch of `batch_frames` frames, frame order kept) out.  Batches are packed into pinned
         buffers and pipelined through `lift_packed_stream`; per-instance point lists stay on the
@@ -397,17 +398,19 @@ class Lifter:
                 yield cur
 
         def batches():
-            # pack batch k+1 (numpy copies into pinned memory, GIL released) while batch k is on the GPU
+            # pack the next batches (numpy copies into pinned memory release the GIL, the descriptor
+            # tables do not) on worker threads while the current one is on the GPU; order is kept
+            from collections import deque
             from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(max_workers=1) as pool:
-                pending = None
+            workers = max(1, int(pack_workers))
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                pending = deque()
                 for g in groups():
-                    nxt = pool.submit(self.pack, g)
-                    if pending is not None:
-                        yield pending.result()
-                    pending = nxt
-                if pending is not None:
-                    yield pending.result()
+                    pending.append(pool.submit(self.pack, g))
+                    if len(pending) > workers:
+                        yield pending.popleft().result()
+                while pending:
+                    yield pending.popleft().result()
 
         t0 = time.time()
         for pb, do, lab in self.lift_packed_stream(batches(), depth=depth, with_handles=True):
