@@ -373,7 +373,7 @@ class Lifter:
 
     @_on_device
     def lift_frame_stream(self, frames, batch_frames: int = 32, timer: Optional[dict] = None, depth: int = 2,
-                          pack_workers: int = 1):
+                          pack_workers: int = 4):
         """Drop-in scripts' entry: an iterator of FrameSpecs in, lists of LiftResult (one list per
         batch of `batch_frames` frames, frame order kept) out.  Batches are packed into pinned
         buffers and pipelined through `lift_packed_stream`; per-instance point lists stay on the
