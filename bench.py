@@ -364,15 +364,19 @@ def run_ours(args, rank, world, local_rank):
             ceil_roots = n_sm * 16 * mhz * 1e6 / 1e9
             roots = pairs
             if screen_modes is not None:
-                modes = screen_modes
+                I_ = m.size
+                modes, g0, g1 = screen_modes[:I_], screen_modes[I_:2 * I_].astype(np.float64), screen_modes[2 * I_:3 * I_].astype(np.float64)
                 mm = m.astype(np.float64)
-                T = np.ceil(mm / 256.0)
-                full_blocks = np.floor(mm / 256.0)
-                # strips J = 0..T-1: rows [0, min(m, 256 (J+1))) x cols of the strip
-                tri = 256.0 * 256.0 * full_blocks * (full_blocks + 1) / 2.0 + (mm - 256.0 * full_blocks) * mm
-                roots = float(np.where(modes == 2, tri, mm * mm).sum())
+
+                def tri(x):      # roots of a symmetric strip sweep over x points: pairs i <= j by 256-column strips
+                    fb = np.floor(x / 256.0)
+                    return 256.0 * 256.0 * fb * (fb + 1) / 2.0 + (x - 256.0 * fb) * x
+                g2 = np.maximum(mm - g0 - g1, 0.0)
+                grouped = tri(g0) + tri(g2) + (mm * mm - g0 * g0 - g2 * g2)      # both groups symmetric, the rest in both orders
+                roots = float(np.where(modes == 2, tri(mm), np.where(modes == 3, grouped, mm * mm)).sum())
                 kern["medoid"]["instances_by_mode"] = {"exact": int((modes == 0).sum()), "screen_all_pairs": int((modes == 1).sum()),
-                                                       "screen_symmetric": int((modes == 2).sum())}
+                                                       "screen_symmetric": int((modes == 2).sum()),
+                                                       "screen_grouped_symmetric": int((modes == 3).sum())}
             kern["medoid"]["bound"] = ("XU pipe: one MUFU.SQRT per evaluated pair distance in the screen pass (reads only "
                                        "sum M points, L2-resident); symmetric instances evaluate the pairs i <= j only")
             kern["medoid"]["square_roots"] = roots

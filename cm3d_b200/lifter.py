@@ -150,9 +150,11 @@ class Lifter:
         self.box_search = None
         self.launches = 0           # kernels launched by this object (bench.py reports it)
         self.screen_min_pts = SCREEN_MIN_PTS   # medoid: instances this large are screened, then verified; 0 = all exact
-        self.screen_flags = 0                  # bit 0: no symmetric screen (every screened instance does all M^2 pairs)
+        self.screen_flags = 0                  # bit 0: no symmetric screen (every screened instance does all M^2 pairs);
+        #                                        bit 1: no grouped symmetric screen for instances that straddle two binades
         self.last_screen_stats = None          # device int32[1]: columns the last run() verified exactly
-        self.last_screen_modes = None          # device int32[I]: 0 exact, 1 screened (all pairs), 2 screened (pairs i <= j)
+        self.last_screen_modes = None          # device int32[3 I]: mode (0 exact, 1 all pairs, 2 symmetric, 3 grouped
+        #                                        symmetric) | points in group 0 | points in the sliver group (mode 3)
         self.timing = None          # dict label -> [(start_event, end_event)] when bench.py profiles
 
     def _call(self, label: str, name: str, *args):
@@ -314,17 +316,18 @@ class Lifter:
             max_items = seg_cap // MEDOID_COLS + 2 * I
             screen = self.screen_min_pts > 0 and not want_col_sums
             screen_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if screen else None
-            screen_min = torch.empty(2 * I, **i32) if screen else None
+            screen_min = torch.empty(5 * I, **i32) if screen else None
+            sym_ws = torch.empty(5 * seg_cap, dtype=torch.float32, device=dev) if screen and not (self.screen_flags & 3) else None
             screen_stats = torch.zeros(1, **i32) if screen else None
             item_pos = torch.empty(max_items, **i32)
             self._call("medoid", "cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), _ptr(seg_point_idx),
                    _ptr(o("item_off")), _ptr(item_inst), I, max_items, _ptr(medoid_best), _ptr(col_sums),
-                   _ptr(screen_sums), _ptr(screen_min), int(self.screen_min_pts) if screen else 0, int(self.screen_flags), _ptr(screen_stats),
-                   _ptr(item_pos),
+                   _ptr(screen_sums), _ptr(screen_min), int(self.screen_min_pts) if screen else 0, int(self.screen_flags), _ptr(sym_ws),
+                   _ptr(screen_stats), _ptr(item_pos),
                    _ptr(o("medoid_local")), _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
-            self.launches += (6 if self.screen_flags & 1 else 9) if screen else 3
+            self.launches += (6 if self.screen_flags & 1 else (9 if self.screen_flags & 2 else 10)) if screen else 3
         self.last_screen_stats = screen_stats
-        self.last_screen_modes = screen_min[I:] if (do_medoid and I and screen_min is not None) else None
+        self.last_screen_modes = screen_min[I:4 * I] if (do_medoid and I and screen_min is not None) else None
         # ---- KITTI: principal-axes box + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479)
         obb = None
         if want_obb is None:

@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 8
+#define CM3D_ABI_VERSION 9
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
@@ -196,13 +196,16 @@ int cm3d_compact_segments(const float *xyzw, const int32_t *tile_cnt, const int3
  * item_off / item_inst: the schedule written by cm3d_scan_segments.
  *
  * Screen + verify (same result, ~3x less work; csrc/medoid.cu has the error bounds): with
- * screen_sums (seg_cap floats), screen_min (2 * n_inst_total words) and screen_min_pts > 0 given and
+ * screen_sums (seg_cap floats), screen_min (5 * n_inst_total words) and screen_min_pts > 0 given and
  * col_sums NULL, instances with screen_min_pts <= M <= 2^19 points get approximate column sums
  * first (bit-identical squared distances, MUFU square root, flat accumulation) and only the
  * columns within the proven error bound of the approximate minimum are summed exactly, in the
  * reference's order; the argmin runs over those.  Instances whose squared norms share one binade
  * (nuScenes' global frame) have an exactly symmetric squared-distance matrix and are screened over
- * the pairs i <= j only (screen_flags bit 0 turns that off).  Smaller instances, instances with
+ * the pairs i <= j only (screen_flags bit 0 turns that off); with sym_ws (5 * seg_cap words of
+ * scratch, optional) instances that straddle two binades are screened the same way on a copy
+ * permuted by binade, pairs across the binades in both orders (bit 1 turns that off).  Smaller
+ * instances, instances with
  * coordinates outside the fast square root's range and every call with col_sums take the all-exact
  * path.  screen_stats (optional, 1 word, zeroed by the caller): receives the number of verified
  * columns.  item_pos (optional scratch, max_items words): item -> schedule position table, so that
@@ -212,7 +215,7 @@ int cm3d_medoid(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off,
                 int n_inst_total,
                 int max_items, unsigned long long *medoid_best, float *col_sums,
                 float *screen_sums, uint32_t *screen_min, int screen_min_pts, int screen_flags,
-                int32_t *screen_stats, int32_t *item_pos, int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
+                float *sym_ws, int32_t *screen_stats, int32_t *item_pos, int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
                 const int32_t *errflags, void *stream);
 #define CM3D_SCREEN_MIN_PTS 512   /* default screen_min_pts */
 

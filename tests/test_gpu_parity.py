@@ -178,7 +178,7 @@ def test_small_segments_all_sizes(lifter):
     p = lambda x: ctypes.c_void_p(x.data_ptr())
     d_inst = torch.arange(n, dtype=torch.int32, device=dev)
     N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), p(d_inst), n, int(item_off[-1]) + 3, p(best), p(col),
-           None, None, 0, 0, None, None,
+           None, None, 0, 0, None, None, None,
            p(ml), p(mp), p(cen), p(err), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     col, ml = col.cpu().numpy(), ml.cpu().numpy()
@@ -209,7 +209,8 @@ def _medoid_abi(pts_list, screen_min_pts, want_sums=False, screen_flags=0):
     best = torch.full((n,), -1, dtype=torch.int64, device=dev)
     col = torch.zeros(cap, dtype=torch.float32, device=dev) if want_sums else None
     ssum = torch.zeros(cap, dtype=torch.float32, device=dev)
-    smin = torch.zeros(2 * n, dtype=torch.int32, device=dev)
+    smin = torch.zeros(5 * n, dtype=torch.int32, device=dev)
+    ws = torch.zeros(5 * cap, dtype=torch.float32, device=dev)
     stats = torch.zeros(1, dtype=torch.int32, device=dev)
     ipos = torch.zeros(int(item_off[-1]) + 3, dtype=torch.int32, device=dev) if screen_min_pts != 32 else None
     ml = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -219,14 +220,14 @@ def _medoid_abi(pts_list, screen_min_pts, want_sums=False, screen_flags=0):
     p = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None else None
     d_inst = torch.arange(n, dtype=torch.int32, device=dev)
     N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), p(d_inst), n, int(item_off[-1]) + 3, p(best), p(col),
-           p(ssum), p(smin), int(screen_min_pts), int(screen_flags), p(stats), p(ipos),
+           p(ssum), p(smin), int(screen_min_pts), int(screen_flags), p(ws), p(stats), p(ipos),
            p(ml), p(mp), p(cen), p(err), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     sums = None
     if want_sums:
         c = col.cpu().numpy()
         sums = [c[seg_off[k]:seg_off[k + 1]] for k in range(n)]
-    _medoid_abi.last_modes = smin.cpu().numpy()[n:]            # 0 exact, 1 screened (all pairs), 2 screened (pairs i <= j)
+    _medoid_abi.last_modes = smin.cpu().numpy()[n:2 * n]      # 0 exact, 1 screened (all pairs), 2 symmetric, 3 grouped symmetric
     return ml.cpu().numpy(), sums, int(stats.item())
 
 
@@ -244,6 +245,15 @@ def _screen_cases():
     for c in ((1024.0, 1024.0, 0.0), (1024.0, 1030.0, 0.0), (1020.0, 1022.0, 0.0)):
         for m in (700, 2600):
             cases.append((rng.normal(0, 1.5, (3, m)) + np.array(c)[:, None]).astype(np.float32))
+    # two clusters on either side of |p|^2 = 2^21, nothing near the boundary: grouped symmetric screen (mode 3);
+    # the same with a few points inside the top sliver of the lower binade (they form the middle group)
+    lo_c = (rng.normal(0, 0.5, (3, 1500)) + np.array([[1020.0], [1022.0], [0.0]])).astype(np.float32)
+    hi_c = (rng.normal(0, 0.5, (3, 900)) + np.array([[1026.0], [1028.0], [0.0]])).astype(np.float32)
+    two = np.concatenate([lo_c, hi_c], 1)[:, rng.permutation(2400)]
+    cases.append(two)
+    sl = np.array([[1024.0, 1023.99988, 1023.9999], [1023.9999, 1024.0, 1023.99988], [0.0, 0.0, 0.0]], np.float32)
+    cases.append(np.concatenate([two[:, :1900], sl, two[:, 1900:]], 1))
+    cases.append(np.concatenate([lo_c[:, :400], hi_c[:, :300]], 1)[:, rng.permutation(700)])
     # sensor-frame instances that ARE symmetric-eligible (one binade of |p|^2, small extent), at several magnitudes
     for c, sg in (((35.0, 2.0, 15.0), 0.5), ((6.0, -1.0, 5.5), 0.15), ((-60.0, 20.0, 1.0), 0.8), ((0.9, 0.1, 0.2), 0.02)):
         for m in (600, 3100):
@@ -294,7 +304,7 @@ def test_medoid_screen_equals_exact(lifter):
     for k in list(range(0, len(cases), 5)) + list(range(len(cases) - 12, len(cases))):
         j, ref = CO.medoid(cases[k], want_sums=True)
         assert np.array_equal(sums[k].view(np.uint32), ref.view(np.uint32)) and exact[k] == j
-    for thr, flags in ((32, 0), (512, 0), (32, 1), (512, 1)):        # flags 1: symmetric screen off
+    for thr, flags in ((32, 0), (512, 0), (32, 1), (512, 1), (32, 2), (512, 2)):   # flags 1: symmetric screens off, 2: grouped off
         got, _, verified = _medoid_abi(cases, thr, screen_flags=flags)
         assert np.array_equal(got, exact), (thr, flags, np.nonzero(got != exact)[0])
         assert verified >= sum(1 for c in cases if c.shape[1] >= thr) - 1     # the out-of-range instance is not screened
@@ -305,14 +315,18 @@ def test_medoid_screen_equals_exact(lifter):
                 assert modes[k] == 0
             elif flags & 1:
                 assert modes[k] in (0, 1)
+            elif flags & 2:
+                assert modes[k] in (0, 1, 2)
         if flags == 0:
             # global-frame clouds around (1200, 950, 1) sit inside one binade of |p|^2: symmetric screen;
             # the ones centred on (1024, 1024, 0) straddle 2^21: all-pairs screen
             g = [k for k, c in enumerate(cases) if c.shape[1] >= 512 and abs(c[0].mean() - 1200) < 1 and abs(c[1].mean() - 950) < 1]
             assert len(g) >= 20 and all(modes[k] == 2 for k in g)
             st = [k for k, c in enumerate(cases) if c.shape[1] >= 700 and c[0].std() > 1.0 and abs(c[0].mean() - 1024) < 0.5 and abs(c[1].mean() - 1024) < 0.5]
-            assert len(st) == 2 and all(modes[k] == 1 for k in st)
+            assert len(st) == 2 and all(modes[k] in (1, 3) for k in st)
             assert (modes == 2).sum() >= 30
+            tw = [k for k, c in enumerate(cases) if c.shape[1] in (2400, 2403, 700) and abs(c[0].mean() - 1022.3) < 0.5 and c[0].std() > 2.0]
+            assert len(tw) == 3 and all(modes[k] == 3 for k in tw), (tw, [modes[k] for k in tw])
     # random segments: the screen leaves about one candidate per instance
     rng = np.random.default_rng(11)
     rnd = [(rng.normal(0, 2, (3, int(m))) + np.array([[900.0], [1500.0], [2.0]])).astype(np.float32)

@@ -45,7 +45,8 @@ def run_case(name, sizes, reps=3, centre=(1200.0, 950.0, 1.0), order_desc=False,
     p = lambda x: ctypes.c_void_p(x.data_ptr())
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     ssum = torch.zeros(cap, dtype=torch.float32, device=dev)
-    smin = torch.zeros(2 * n, dtype=torch.int32, device=dev)
+    smin = torch.zeros(5 * n, dtype=torch.int32, device=dev)
+    ws = torch.zeros(5 * cap, dtype=torch.float32, device=dev)
     flags = int(os.environ.get("CM3D_SCREEN_FLAGS", "0"))
     ipos = torch.zeros(int(item_off[-1]) + 1, dtype=torch.int32, device=dev)
     screen = int(os.environ.get("CM3D_SCREEN_MIN_PTS", "512"))
@@ -53,7 +54,7 @@ def run_case(name, sizes, reps=3, centre=(1200.0, 950.0, 1.0), order_desc=False,
     def launch():
         best.fill_(-1)
         N.call("cm3d_medoid", p(d_xyzw), cap, p(d_off), p(d_idx), p(d_item), p(d_inst), n, int(item_off[-1]), p(best),
-               None, p(ssum), p(smin), screen, flags, None, p(ipos), p(ml), p(mp), p(cen), p(err), st)
+               None, p(ssum), p(smin), screen, flags, p(ws), None, p(ipos), p(ml), p(mp), p(cen), p(err), st)
     launch()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
