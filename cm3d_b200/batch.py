@@ -104,6 +104,66 @@ def cull_planes(cam, W: int, H: int, min_dist32, tref):
     return out32, flags
 
 
+def cull_planes_many(cams, sizes, min_dist32, tref):
+    """cull_planes for all vcams of a frame at once (same arithmetic on stacked arrays; they share the
+    kinds of their chain, the caller checks that).  cams: CamSpecs, sizes: (W, H) per vcam.
+    Returns (planes[V,5,4] f32, flags[V])."""
+    V = len(cams)
+    K = np.stack([np.asarray(c.K, np.float64) for c in cams])                   # (V,3,3)
+    bottom_ok = (K[:, 2, 0] == 0) & (K[:, 2, 1] == 0) & (K[:, 2, 2] == 1)
+    simple = (K[:, 0, 1] == 0) & (K[:, 1, 0] == 0) & (K[:, 0, 0] != 0) & (K[:, 1, 1] != 0) & bottom_ok
+    M = np.broadcast_to(_I3, (V, 3, 3))
+    c = np.zeros((V, 3))
+    tau = np.zeros(V)
+    ok = np.ones(V, bool)
+    kinds = [k for k, _ in cams[0].ops]
+    for k, kind in enumerate(kinds):
+        m = np.stack([np.asarray(cam.ops[k][1], np.float64) for cam in cams])
+        if kind == "T":
+            c = c + m
+            if k:
+                tau = tau + np.abs(m).sum(1)
+        else:
+            L = m if kind == "R" else m[:, :, :3]
+            ok &= np.abs(L @ L.transpose(0, 2, 1) - _I3).reshape(V, 9).max(1) < 1e-3
+            M, c = L @ M, (L @ c[:, :, None])[:, :, 0]
+            if kind == "A":
+                c = c + m[:, :, 3]
+                tau = tau + np.abs(m[:, :, 3]).sum(1)
+    tref = np.asarray(tref, np.float64)
+    if kinds and kinds[0] == "T":
+        t0 = tref + np.stack([np.asarray(cam.ops[0][1], np.float64) for cam in cams])
+        tau = tau + np.abs(t0).sum(1)
+    else:
+        tau = tau + np.abs(tref).sum()
+    c2 = c - M @ tref                                                           # p = q - tref
+    W = np.array([s[0] for s in sizes], np.float64)
+    H = np.array([s[1] for s in sizes], np.float64)
+    abc = np.empty((V, 5, 3))
+    abc[:, 0] = (0.0, 0.0, 1.0)
+    abc[:, 1] = K[:, 0]
+    abc[:, 2, :2], abc[:, 2, 2] = -K[:, 0, :2], W - K[:, 0, 2]
+    abc[:, 3] = K[:, 1]
+    abc[:, 4, :2], abc[:, 4, 2] = -K[:, 1, :2], H - K[:, 1, 2]
+    d0 = np.zeros((V, 5))
+    d0[:, 0] = -float(min_dist32)
+    kappa = 1.75 * np.abs(abc).sum(2)                                            # (V,5)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        n = (abc @ M) / kappa[:, :, None]
+        d = ((abc @ c2[:, :, None])[:, :, 0] + d0) / kappa
+    good = ok & bottom_ok & np.isfinite(M).reshape(V, 9).all(1) & (np.abs(n).sum(2) <= 1.0).all(1) & np.isfinite(d).all(1)
+    with np.errstate(invalid="ignore"):
+        mg0 = 2.0 ** -17 * tau + 2.0 ** -20 * np.abs(d).max(1) + 1e-30
+    out = np.empty((V, 5, 4))
+    out[:, :, :3] = n
+    out[:, :, 3] = d + mg0[:, None]
+    with np.errstate(invalid="ignore", over="ignore"):
+        out32 = out.astype(np.float32)
+    out32[:, :, 3] = np.nextafter(out32[:, :, 3], np.float32(np.inf))           # rounding of d never tightens a plane
+    out32[~good] = _OFF_PLANES
+    return out32, simple.astype(np.int32)
+
+
 def _chain_sig(ops) -> int:
     kinds = {"T": 1, "R": 2, "A": 3}
     return sum(kinds[k] << (2 * i) for i, (k, _) in enumerate(ops))
@@ -236,10 +296,16 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
         first = f.cams[keys[0][0]].ops if keys else []
         tref = np.asarray(first[0][1], np.float32) if (first and first[0][0] == "T") else np.zeros(3, np.float32)
         sigs = {_chain_sig(f.cams[k[0]].ops) for k in keys}
-        for k, mem in zip(keys, members):
+        vcams = [f.cams[k[0]] for k in keys]
+        if len(vcams) > 1 and len({tuple(kind for kind, _ in c.ops) for c in vcams}) == 1:
+            planes_all, flags_all = cull_planes_many(vcams, [(k[1], k[2]) for k in keys], f.min_dist_f32(), tref)
+        else:
+            pf = [cull_planes(c, k[1], k[2], f.min_dist_f32(), tref) for c, k in zip(vcams, keys)]
+            planes_all, flags_all = [a for a, _ in pf], [b for _, b in pf]
+        for vi, (k, mem) in enumerate(zip(keys, members)):
             cam = f.cams[k[0]]
             row = np.zeros(VC_WORDS, np.int32)
-            planes, flags = cull_planes(cam, k[1], k[2], f.min_dist_f32(), tref)
+            planes, flags = planes_all[vi], int(flags_all[vi])
             row[20:40] = planes.reshape(-1).view(np.int32)
             row[40] = flags
             row[0] = len(chains)

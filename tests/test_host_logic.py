@@ -259,3 +259,27 @@ def test_cull_planes_random_cameras_and_boundary_points():
         n_culled += int((val < -Sq * 2.0 ** -17).any(0).sum())
         n_pairs += n
     assert n_inside > 20000 and n_culled > 0.2 * n_pairs
+
+
+def test_cull_planes_many_equals_per_camera():
+    """The per-frame (stacked) cull-plane computation gives the per-camera function's planes and flags,
+    including the switched-off planes of a camera whose chain is not rigid."""
+    from cm3d_b200 import synthetic as S
+    from cm3d_b200.batch import cull_planes, cull_planes_many
+    from cm3d_b200.frames import op_R
+    for cfg in ("c1", "c4"):
+        f = S.make_frame(cfg, 3, scale=0.05, mask_div=4)
+        cams = list(f.cams.values()) if isinstance(f.cams, dict) else list(f.cams)
+        first = cams[0].ops
+        tref = np.asarray(first[0][1], np.float32) if first[0][0] == "T" else np.zeros(3, np.float32)
+        # make one camera's rotation non-orthogonal: its planes must come back switched off
+        bad = cams[1]
+        k = [i for i, (kind, _) in enumerate(bad.ops) if kind == "R"][0]
+        bad.ops[k] = op_R(np.asarray(bad.ops[k][1]) * 1.01)
+        sizes = [(1024, 576 + 7 * i) for i in range(len(cams))]
+        pm, fm = cull_planes_many(cams, sizes, f.min_dist_f32(), tref)
+        for v, c in enumerate(cams):
+            p1, f1 = cull_planes(c, sizes[v][0], sizes[v][1], f.min_dist_f32(), tref)
+            assert f1 == fm[v]
+            assert np.allclose(p1, pm[v], rtol=1e-6, atol=0)
+        assert np.array_equal(pm[1], np.tile(np.array([0, 0, 0, 1], np.float32), (5, 1)))
