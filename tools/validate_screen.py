@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Screened medoid (screen + verify) against the all-exact kernel on bench-sized batches.
 
-    python tools/validate_screen.py [n_frames=64] [first_index=0]
+    python tools/validate_screen.py [n_frames=64] [first_index=0] [config=c2|c3|c4]
 
 Prints the number of instances compared, how many went through the screen, the number of columns the
 verify pass summed exactly, and any disagreement (there must be none)."""
@@ -17,7 +17,12 @@ def main():
     from cm3d_b200.lifter import Lifter
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    frames = bench.make_frames(first, n, 16)
+    cfg = sys.argv[3] if len(sys.argv) > 3 else "c2"
+    if cfg == "c2":
+        frames = bench.make_frames(first, n, 16)
+    else:
+        from cm3d_b200 import synthetic as S
+        frames = [S.make_frame(cfg, first + i) for i in range(n)]
     lifter = Lifter("cuda:0")
     pb = lifter.pack(frames)
     db = lifter.upload(pb)
@@ -33,7 +38,7 @@ def main():
     m = out[0][3]
     for thr in (512, 32):
         bad = np.flatnonzero(out[thr][0] != out[0][0])
-        print(f"screen_min_pts={thr}: {m.size} instances, {int((m >= max(thr, 32)).sum())} screened, "
+        print(f"{cfg} frames {first}..{first + n - 1} screen_min_pts={thr}: {m.size} instances, {int((m >= max(thr, 32)).sum())} screened, "
               f"{out[thr][2]} columns verified, {bad.size} disagreements {bad[:10].tolist()}", flush=True)
         assert bad.size == 0 and np.array_equal(out[thr][1], out[0][1])
 
