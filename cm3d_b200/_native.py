@@ -38,6 +38,8 @@ PROTOTYPES = {
     "cm3d_nearest_lane": [_P, _I, _P, _I, _P, _P, _P],
     "cm3d_selftest_sqrt": [_P, _P],
     "cm3d_selftest_sqrt_approx": [_P, _P],
+    "cm3d_pack_plan": [_P, _P],
+    "cm3d_pack_fill": [_P, _P, _P, _P, _P, _P, _P, _P],
 }
 EXPORTS = ["cm3d_abi_version", "cm3d_error_string"] + list(PROTOTYPES)
 

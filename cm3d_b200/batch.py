@@ -169,9 +169,44 @@ def _chain_sig(ops) -> int:
     return sum(kinds[k] << (2 * i) for i, (k, _) in enumerate(ops))
 
 
-def _alloc(n, dtype, pin):
-    """Host buffer of n elements; pinned torch memory when asked and possible."""
+class PinnedPool:
+    """Reusable pinned host buffers for the packers (cudaHostAlloc is slow and serialises the packer threads).
+    take() hands out a pinned uint8 tensor of at least `nbytes`; give() returns it once the batch's
+    host->device copies are done (PackedBatch.release)."""
+
+    def __init__(self):
+        import threading
+        self._lock = threading.Lock()
+        self._free = []
+
+    def take(self, nbytes: int):
+        import torch
+        nbytes = max(int(nbytes), 16)
+        with self._lock:
+            best = -1
+            for k, t in enumerate(self._free):           # smallest buffer that fits, but not a giant for a small request
+                if nbytes <= t.numel() <= max(4 * nbytes, 1 << 16) and (best < 0 or t.numel() < self._free[best].numel()):
+                    best = k
+            if best >= 0:
+                return self._free.pop(best)
+        return torch.empty((nbytes * 5 // 4 + 4095) & ~4095, dtype=torch.uint8, pin_memory=True)     # head room: batches vary
+
+    def give(self, tensors):
+        with self._lock:
+            self._free.extend(tensors)
+            if len(self._free) > 64:                      # keep the largest ones
+                self._free = sorted(self._free, key=lambda x: -x.numel())[:64]
+
+
+def _alloc(n, dtype, pin, pool=None, taken=None):
+    """Host buffer of n elements; pinned torch memory when asked and possible (from `pool` when given)."""
     n = max(int(n), 1)
+    if pin and pool is not None:
+        import torch
+        base = pool.take(n * np.dtype(dtype).itemsize)
+        taken.append(base)
+        t = base[:n * np.dtype(dtype).itemsize].view(getattr(torch, np.dtype(dtype).name))
+        return t.numpy(), t
     if pin:
         import torch
         t = torch.empty(n, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
@@ -212,6 +247,14 @@ class PackedBatch:
         o, n = self.off[name], self.off[name + "_n"]
         v = self.meta[o:o + n]
         return v.reshape(-1, words) if words > 1 else v
+
+    def release(self):
+        """Hand the pinned buffers back to the pool they came from (after the host->device copies are done;
+        the batch's host arrays must not be used afterwards).  No-op for batches that own their memory."""
+        pool, taken = getattr(self, "_pool", None), getattr(self, "_taken", None)
+        if pool is not None and taken:
+            self._pool = self._taken = None
+            pool.give(taken)
 
     @property
     def h2d_bytes(self) -> int:
@@ -397,4 +440,124 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
     pb.any_kitti = any(f.dataset == "kitti" for f in frames)
     pb.frame_datasets = [f.dataset for f in frames]
     pb.grid_words, pb.max_cells = grid_words, max_cells
+    return pb
+
+
+# ------------------------------------------------------------------------------------------ native packer
+_KIND_CODE = {"T": 1, "R": 2, "A": 3}
+
+
+def _ptr_of(a: np.ndarray) -> int:
+    return a.__array_interface__["data"][0]
+
+
+def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "PinnedPool" = None) -> PackedBatch:
+    """pack_frames through the C packer of the library (csrc/pack.cu): the FrameSpecs are flattened into
+    pointer / size arrays here, everything else - the copy of the raw sweeps into (pinned) memory, the
+    descriptor tables, the fp64 cull planes - happens in one ctypes call that holds no GIL, so several
+    batches are packed at once by worker threads.  Same buffers as pack_frames (tests/test_host_logic.py).
+    Batches it does not cover (dense masks, decoded run lengths, no instances at all) go to pack_frames."""
+    import ctypes
+    from . import _native as N
+    F = len(frames)
+    if F == 0:
+        raise ValueError("empty batch")
+    for f in frames:
+        if isinstance(f.masks, np.ndarray) or any(not isinstance(m.counts, (bytes, str)) for m in f.masks):
+            return pack_frames(frames, pin)
+    if not any(f.n_instances for f in frames):
+        return pack_frames(frames, pin)
+    lib = N.load()
+
+    sw_ptr, sw_npts, sw_stride, op_begin, op_kind, op_ptr, cam_K = [], [], [], [0], [], [], []
+    keep = []                                    # arrays whose memory the C side reads
+    for f in frames:
+        for s, ops in zip(f.sweeps, f.sweep_ops):
+            sw_ptr.append(_ptr_of(s)); sw_npts.append(s.shape[0]); sw_stride.append(s.shape[1])
+            for kind, m in ops:
+                op_kind.append(_KIND_CODE[kind]); op_ptr.append(_ptr_of(m))
+            op_begin.append(len(op_kind))
+    for f in frames:
+        for cam in f.cams:
+            for kind, m in cam.ops:
+                op_kind.append(_KIND_CODE[kind]); op_ptr.append(_ptr_of(m))
+            op_begin.append(len(op_kind))
+            cam_K.append(_ptr_of(cam.K))
+    counts = []
+    for f in frames:
+        for m in f.masks:
+            c = m.counts
+            counts.append(c.encode("ascii") if isinstance(c, str) else c)
+    blob = b"".join(counts)
+    in_counts_off = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(np.fromiter(map(len, counts), np.int64, len(counts)), out=in_counts_off[1:])
+    n_inst = len(counts)
+    in_cam = np.concatenate([f.cam_nums for f in frames]).astype(np.int32) if n_inst else np.zeros(1, np.int32)
+    sizes = np.array([m.size for f in frames for m in f.masks], np.int32).reshape(-1, 2) if n_inst else np.zeros((1, 2), np.int32)
+    in_W, in_H = np.ascontiguousarray(sizes[:, 0]), np.ascontiguousarray(sizes[:, 1])
+
+    i32 = lambda v: np.asarray(v, np.int32)
+    f32 = lambda v: np.asarray(v, np.float32)
+    arrs = dict(
+        fr_n_sweeps=i32([len(f.sweeps) for f in frames]), fr_n_cams=i32([len(f.cams) for f in frames]),
+        fr_n_inst=i32([f.n_instances for f in frames]), fr_fourth=i32([f.fourth for f in frames]),
+        fr_min_pts=i32([4 if f.dataset == "kitti" else 1 for f in frames]),
+        fr_use_close=i32([f.close_thresh is not None for f in frames]),
+        fr_use_floor=i32([f.floor_thresh is not None for f in frames]),
+        fr_close=f32([0.0 if f.close_thresh is None else f.close_thresh for f in frames]),
+        fr_min_dist=f32([f.min_dist_f32() for f in frames]),
+        fr_floor=f32([0.0 if f.floor_thresh is None else f.floor_thresh for f in frames]),
+        sw_ptr=np.asarray(sw_ptr, np.uint64), sw_npts=i32(sw_npts), sw_stride=i32(sw_stride),
+        op_begin=i32(op_begin), op_kind=i32(op_kind), op_ptr=np.asarray(op_ptr, np.uint64),
+        cam_K=np.asarray(cam_K, np.uint64), in_cam=in_cam, in_W=in_W, in_H=in_H, in_counts_off=in_counts_off)
+    for f in frames:
+        if len(f.sweeps) and any(len(o) > 4 for o in f.sweep_ops):
+            return pack_frames(frames, pin)
+
+    class _In(ctypes.Structure):
+        _fields_ = [("n_frames", ctypes.c_int32), ("n_sweeps", ctypes.c_int32), ("n_cams", ctypes.c_int32),
+                    ("n_inst", ctypes.c_int32)] + [(k, ctypes.c_void_p) for k in (
+                        "fr_n_sweeps", "fr_n_cams", "fr_n_inst", "fr_fourth", "fr_min_pts", "fr_use_close", "fr_use_floor",
+                        "fr_close", "fr_min_dist", "fr_floor", "sw_ptr", "sw_npts", "sw_stride", "op_begin", "op_kind",
+                        "op_ptr", "cam_K", "in_cam", "in_W", "in_H", "in_counts_off", "counts")]
+    inp = _In(F, len(sw_ptr), len(cam_K), n_inst)
+    for k, a in arrs.items():
+        setattr(inp, k, _ptr_of(a))
+    inp.counts = ctypes.cast(ctypes.c_char_p(blob), ctypes.c_void_p).value
+    plan = np.zeros(16, np.int64)
+    rc = lib.cm3d_pack_plan(ctypes.byref(inp), ctypes.c_void_p(_ptr_of(plan)))
+    if rc != 0:
+        return pack_frames(frames, pin)          # raises the per-frame limit error with its message
+    n_tiles, n_vcams, n_chains = int(plan[0]), int(plan[1]), int(plan[2])
+    taken = []
+    raw, raw_t = _alloc(int(plan[3]), np.float32, pin, pool, taken)
+    meta, meta_t = _alloc(int(plan[4]), np.int32, pin, pool, taken)
+    mask, mask_t = _alloc(int(plan[5]), np.uint8, pin, pool, taken)
+    mo, mo_t = _alloc(n_inst + 1, np.int64, pin, pool, taken)
+    vkeys = np.zeros((max(n_vcams, 1), 4), np.int32)
+    out = np.zeros(8, np.int64)
+    rc = lib.cm3d_pack_fill(ctypes.byref(inp), ctypes.c_void_p(_ptr_of(plan)), ctypes.c_void_p(_ptr_of(raw)),
+                            ctypes.c_void_p(_ptr_of(meta)), ctypes.c_void_p(_ptr_of(mask)), ctypes.c_void_p(_ptr_of(mo)),
+                            ctypes.c_void_p(_ptr_of(vkeys)), ctypes.c_void_p(_ptr_of(out)))
+    N.check(rc, "cm3d_pack_fill")
+    names = ["tile_sweep", "sweep_desc", "frame_desc", "vcam_desc", "cam_inst_list", "inst_desc", "chains"]
+    lens = [max(n_tiles, 1), max(len(sw_ptr), 1) * SW_WORDS, F * FR_WORDS, max(n_vcams, 1) * VC_WORDS, max(n_inst, 1),
+            max(n_inst, 1) * IN_WORDS, max(n_chains, 1) * CHAIN_WORDS]
+    off = {}
+    for k, (name, n) in enumerate(zip(names, lens)):
+        off[name] = int(plan[6 + k])
+        off[name + "_n"] = int(n)
+    frame_inst = np.zeros(F + 1, np.int64)
+    np.cumsum(arrs["fr_n_inst"], out=frame_inst[1:])
+    frame_vcam_cams = [[] for _ in range(F)]
+    for fr, cam, W, H in vkeys[:n_vcams].tolist():
+        frame_vcam_cams[fr].append((cam, W, H))
+    pb = PackedBatch(F, len(sw_ptr), n_tiles, n_vcams, n_inst, n_chains, int(plan[13]), int(out[0]), int(out[1]),
+                     int(out[2]), int(plan[14]), "rle_str", int(out[5]), raw, meta, mask, mo[:n_inst + 1], off, frame_inst,
+                     frame_vcam_cams, {"raw": raw_t, "meta": meta_t, "mask": mask_t, "mask_off": mo_t})
+    pb.any_kitti = any(f.dataset == "kitti" for f in frames)
+    pb.frame_datasets = [f.dataset for f in frames]
+    pb.grid_words, pb.max_cells = int(out[3]), int(out[4])
+    if pool is not None and taken:
+        pb._pool, pb._taken = pool, taken
     return pb

@@ -16,7 +16,8 @@ import numpy as np
 import torch
 
 from . import _native as N
-from .batch import ERR_WORDS, FR_WORDS, MAX_INST, MEDOID_COLS, SCREEN_MIN_PTS, TILE, PackedBatch, pack_frames
+from .batch import (ERR_WORDS, FR_WORDS, MAX_INST, MEDOID_COLS, SCREEN_MIN_PTS, TILE, PackedBatch, pack_frames,
+                    pack_frames_native, PinnedPool)
 from .frames import FrameSpec, LiftResult
 
 
@@ -146,6 +147,7 @@ class Lifter:
         self._streams = None        # (copy, compute) streams of the pipelined path, created once: torch's
         #                             caching allocator pools memory per stream, so fresh streams per call
         #                             would cudaMalloc the whole workspace again (~100 ms)
+        self._pin_pool = None       # pinned host buffers of the streaming path, reused across batches
         self.denoise = None         # default-off extensions, see run()
         self.box_search = None
         self.launches = 0           # kernels launched by this object (bench.py reports it)
@@ -170,7 +172,14 @@ class Lifter:
 
     # ------------------------------------------------------------------ host -> device
     def pack(self, frames: Sequence[FrameSpec]) -> PackedBatch:
-        return pack_frames(frames, pin=True)
+        # the C packer (csrc/pack.cu) for batches whose masks are counts strings, the Python packer otherwise
+        return pack_frames_native(frames, pin=True)
+
+    def _pack_pooled(self, frames: Sequence[FrameSpec]) -> PackedBatch:
+        """pack() into pinned buffers of this Lifter's pool; the streaming path releases them after use."""
+        if self._pin_pool is None:
+            self._pin_pool = PinnedPool()
+        return pack_frames_native(frames, pin=True, pool=self._pin_pool)
 
     @_on_device
     def upload(self, pb: PackedBatch) -> DeviceBatch:
@@ -409,7 +418,7 @@ class Lifter:
             with ThreadPoolExecutor(max_workers=workers) as pool:
                 pending = deque()
                 for g in groups():
-                    pending.append(pool.submit(self.pack, g))
+                    pending.append(pool.submit(self._pack_pooled, g))
                     if len(pending) > workers:
                         yield pending.popleft().result()
                 while pending:
@@ -418,6 +427,7 @@ class Lifter:
         t0 = time.time()
         for pb, do, lab in self.lift_packed_stream(batches(), depth=depth, with_handles=True):
             res = merge_split(self.results(do, lab, with_points=False), part_queue.pop(0))
+            pb.release()                        # its pinned buffers go back to the pool: the copies are long done
             if timer is not None:
                 timer["points in mask"] += time.time() - t0
             yield res

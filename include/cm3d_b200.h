@@ -282,6 +282,36 @@ int cm3d_selftest_sqrt(unsigned long long *mismatches, void *stream);
  * screen error bound assumes <= 4; the GPU suite pins <= 2. */
 int cm3d_selftest_sqrt_approx(unsigned *max_ulp, void *stream);
 
+/* ---- host-side packer (no CUDA call inside; releases nothing, allocates nothing the caller sees) ---------- */
+
+/* The batch as flat arrays (cm3d_b200/batch.py: pack_frames_native builds it from FrameSpecs).  Ops of all
+ * chains back to back: the sweeps' chains in sweep order, then the cameras' chains in camera order
+ * (frame-major); op_begin has n_sweeps + n_cams + 1 entries; pointers travel as 64-bit integers. */
+typedef struct cm3d_pack_input {
+    int32_t n_frames, n_sweeps, n_cams, n_inst;
+    const int32_t *fr_n_sweeps, *fr_n_cams, *fr_n_inst, *fr_fourth, *fr_min_pts, *fr_use_close, *fr_use_floor;
+    const float *fr_close, *fr_min_dist, *fr_floor;
+    const uint64_t *sw_ptr;
+    const int32_t *sw_npts, *sw_stride;
+    const int32_t *op_begin, *op_kind;
+    const uint64_t *op_ptr;
+    const uint64_t *cam_K;
+    const int32_t *in_cam, *in_W, *in_H;
+    const int64_t *in_counts_off;
+    const uint8_t *counts;
+} cm3d_pack_input;
+
+/* plan[16]: 0 n_tiles, 1 n_vcams, 2 n_chains, 3 raw floats, 4 meta words, 5 mask bytes, 6..12 word offsets of
+ * tile_sweep, sweep_desc, frame_desc, vcam_desc, cam_inst_list, inst_desc, chains in meta, 13 max instances per
+ * frame, 14 raw points.  CM3D_ELIMIT when a frame exceeds CM3D_MAX_INST / CM3D_MAX_VCAMS. */
+int cm3d_pack_plan(const cm3d_pack_input *in, int64_t *plan);
+
+/* Fills raw (plan[3] floats), meta (plan[4] words), mask (plan[5] bytes: the counts strings), mask_off
+ * (n_inst + 1), vcam_keys (plan[1] x {frame, camera, W, H}) and out[8] = cnt_total, bits_words, max_words,
+ * grid_words, max_cells, max_runs.  Same bytes as the Python packer (cull planes to fp64 rounding). */
+int cm3d_pack_fill(const cm3d_pack_input *in, const int64_t *plan, float *raw, int32_t *meta, uint8_t *mask,
+                   int64_t *mask_off, int32_t *vcam_keys, int64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,3 +283,40 @@ def test_cull_planes_many_equals_per_camera():
             assert f1 == fm[v]
             assert np.allclose(p1, pm[v], rtol=1e-6, atol=0)
         assert np.array_equal(pm[1], np.tile(np.array([0, 0, 0, 1], np.float32), (5, 1)))
+
+
+def test_native_packer_equals_python_packer():
+    """csrc/pack.cu (cm3d_pack_plan / cm3d_pack_fill through pack_frames_native) writes the buffers the Python
+    packer writes: every descriptor table, the raw sweeps, the counts strings and the scalar geometry are
+    identical; the fp64 cull planes agree to fp32 rounding (numpy's 3x3 products may associate differently)."""
+    import dataclasses
+    from cm3d_b200 import synthetic as S
+    from cm3d_b200 import batch as B
+    from cm3d_b200.synthetic import compress_rles, dense_to_rle
+    frames = [S.make_frame("c1", 0, scale=0.1, mask_div=2), S.make_frame("c2", 1, scale=0.05, mask_div=2),
+              S.make_frame("c3", 2, scale=0.1, mask_div=2), S.make_frame("c4", 3, scale=0.05, mask_div=2)]
+    for f in frames:                      # the on-disk mask format: compressed counts strings
+        if isinstance(f.masks, np.ndarray):
+            f.masks = compress_rles(dense_to_rle(f.masks))
+        elif not all(isinstance(m.counts, (bytes, str)) for m in f.masks):
+            f.masks = compress_rles(f.masks)
+    empty = dataclasses.replace(frames[0], sweeps=[np.zeros((0, 5), np.float32)] + frames[0].sweeps[1:])
+    for batch in (frames, frames[:1], [frames[2]], [empty, frames[1]]):
+        a, b = B.pack_frames(batch), B.pack_frames_native(batch)
+        assert b.masks_kind == "rle_str" == a.masks_kind
+        for name in ("n_frames", "n_sweeps", "n_tiles", "n_vcams", "n_inst", "n_chains", "max_inst_per_frame", "cnt_total",
+                     "bits_words", "max_words", "n_raw_points", "max_runs", "grid_words", "max_cells", "any_kitti",
+                     "frame_datasets", "frame_vcam_cams"):
+            assert getattr(a, name) == getattr(b, name), name
+        assert np.array_equal(a.frame_inst, b.frame_inst)
+        assert np.array_equal(a.raw.view(np.uint32), b.raw.view(np.uint32))
+        assert np.array_equal(a.mask, b.mask) and np.array_equal(a.mask_off, b.mask_off)
+        for name, words in (("tile_sweep", 1), ("sweep_desc", B.SW_WORDS), ("frame_desc", B.FR_WORDS), ("cam_inst_list", 1),
+                            ("inst_desc", B.IN_WORDS), ("chains", B.CHAIN_WORDS)):
+            assert a.off[name + "_n"] == b.off[name + "_n"], name
+            assert np.array_equal(a.table(name, words), b.table(name, words)), name
+        va, vb = a.table("vcam_desc", B.VC_WORDS), b.table("vcam_desc", B.VC_WORDS)
+        assert np.array_equal(va[:, :20], vb[:, :20]) and np.array_equal(va[:, 40:], vb[:, 40:])
+        pa, pb_ = va[:, 20:40].copy().view(np.float32), vb[:, 20:40].copy().view(np.float32)
+        assert np.allclose(pa, pb_, rtol=2e-6, atol=0)
+        assert (pa != pb_).mean() < 0.2          # mostly bit-identical
