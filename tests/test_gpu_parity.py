@@ -701,3 +701,26 @@ def test_randomised_geometry_against_c_oracle(lifter):
             _check_vs_c_oracle(f, r)
             n_member += int(r.seg_offsets[-1])
     assert n_member > 3000
+
+
+def test_frame_stream_with_packer_threads_and_buffer_pool(lifter):
+    """lift_frame_stream (C packer on worker threads, pooled pinned buffers handed back after every batch)
+    returns, frame by frame, what the synchronous lift_frames returns - also when a later batch reuses the
+    pinned memory of an earlier one."""
+    from cm3d_b200 import synthetic as S
+    from cm3d_b200.synthetic import compress_rles, dense_to_rle
+    frames = [S.make_frame("c1" if i % 3 else "c2", 40 + i, scale=0.2 if i % 3 else 0.08, mask_div=2) for i in range(13)]
+    for f in frames:                      # the on-disk mask format (counts strings): the C packer's input
+        f.masks = compress_rles(dense_to_rle(f.masks) if isinstance(f.masks, np.ndarray) else f.masks)
+    want = lifter.lift_frames(frames, with_points=False)
+    for workers in (1, 3):
+        got = []
+        for batch in lifter.lift_frame_stream(iter(frames), batch_frames=2, pack_workers=workers):
+            got.extend(batch)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert a.n_points == b.n_points
+            assert np.array_equal(a.seg_offsets, b.seg_offsets)
+            assert np.array_equal(a.medoid_point_idx, b.medoid_point_idx)
+            assert np.array_equal(a.centroids.view(np.uint32), b.centroids.view(np.uint32))
+    assert lifter._pin_pool is not None and len(lifter._pin_pool._free) >= 4
