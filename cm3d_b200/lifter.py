@@ -250,7 +250,7 @@ class Lifter:
                 row_range = torch.empty(2 * I, **i32)
                 self._call("masks_rle", "cm3d_masks_fill_rle", _ptr(runs), _ptr(db.mask_off), _ptr(run_start), _ptr(inst_desc),
                        I, pb.max_runs, _ptr(bits_raw), _ptr(row_range), _ptr(o("errflags")), st)
-                self.launches += 3
+                self.launches += 2              # k_rle_prefix, k_rle_fill (torch's zero fill of the planes is not ours)
             self._call("masks_erode", "cm3d_masks_erode3x3", _ptr(bits_raw), _ptr(inst_desc), _ptr(row_range), I,
                        pb.max_words, _ptr(bits), _ptr(bbox), st)
             self.launches += 2
@@ -334,7 +334,8 @@ class Lifter:
                    _ptr(screen_sums), _ptr(screen_min), int(self.screen_min_pts) if screen else 0, int(self.screen_flags), _ptr(sym_ws),
                    _ptr(screen_stats), _ptr(item_pos),
                    _ptr(o("medoid_local")), _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
-            self.launches += (6 if self.screen_flags & 1 else (9 if self.screen_flags & 2 else 10)) if screen else 3
+            # expand_items, k_medoid, finalize; + classify, screen, verify; + screen_sym, screen_min; + permute
+            self.launches += (6 if self.screen_flags & 1 else (8 if self.screen_flags & 2 else 9)) if screen else 3
         self.last_screen_stats = screen_stats
         self.last_screen_modes = screen_min[I:4 * I] if (do_medoid and I and screen_min is not None) else None
         # ---- KITTI: principal-axes box + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479)
