@@ -148,6 +148,7 @@ class Lifter:
         #                             caching allocator pools memory per stream, so fresh streams per call
         #                             would cudaMalloc the whole workspace again (~100 ms)
         self._pin_pool = None       # pinned host buffers of the streaming path, reused across batches
+        self._seg_ratio = None      # largest member-points / raw-points ratio the streaming path has seen
         self.denoise = None         # default-off extensions, see run()
         self.box_search = None
         self.launches = 0           # kernels launched by this object (bench.py reports it)
@@ -218,7 +219,10 @@ class Lifter:
         F, I, T = pb.n_frames, pb.n_inst, pb.n_tiles
         n_slots = max(T, 1) * TILE
         if seg_cap is None:
-            seg_cap = int(self.seg_factor * pb.n_raw_points) + 1024
+            # members per raw point: the configured bound until the streaming path has seen batches, then 1.5 x the
+            # largest ratio seen (+5 %); a batch that does not fit is rerun with its exact size (check_flags)
+            factor = self.seg_factor if self._seg_ratio is None else min(self.seg_factor, 1.5 * self._seg_ratio + 0.05)
+            seg_cap = int(factor * pb.n_raw_points) + 1024
         seg_cap = (int(seg_cap) + 3) & ~3
         i32 = dict(dtype=torch.int32, device=dev)
         lay = self._out_layout(F, I)
@@ -456,6 +460,9 @@ class Lifter:
             lab = self._split_labels(pinned[:do.out.numel()].numpy().copy(), do.layout)
             pool.append(pinned)
             need = self.check_flags(lab)
+            if pb.n_raw_points:
+                ratio = max(need, int(lab["seg_off"][-1])) / pb.n_raw_points
+                self._seg_ratio = ratio if self._seg_ratio is None else max(0.95 * self._seg_ratio, ratio)
             if need:                        # rare: rerun this batch synchronously with exact capacity
                 with torch.cuda.stream(comp_s):
                     do = self.run(db, seg_cap=need)
