@@ -278,8 +278,11 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
     n_inst = sum(f.n_instances for f in frames)
     sweep_tiles, raw_off = [], []
     ro = 0
+    def packed(s):      # nuScenes rows are (x, y, z, intensity, ring index): the fifth column is never read
+        return s[:, :4] if s.shape[1] == 5 else s
     for f in frames:
         for s in f.sweeps:
+            s = packed(s)
             if s.shape[0] == 0:
                 sweep_tiles.append(0)
                 raw_off.append(ro)
@@ -313,6 +316,7 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
         max_inst_pf = max(max_inst_pf, I)
         t_begin = ti
         for s_local, (s, ops) in enumerate(zip(f.sweeps, f.sweep_ops)):
+            s = packed(s)
             nt = sweep_tiles[si]
             o = raw_off[si]
             raw[o:o + s.size] = s.reshape(-1)

@@ -69,9 +69,15 @@ k_aggregate(const float *__restrict__ raw, const int32_t *__restrict__ tile_swee
         bool keep = p < npts;
         float x = 0.f, y = 0.f, z = 0.f, w = 1.0f;
         if (keep) {
-            const float *q = s_raw + p * stride;
-            x = q[0]; y = q[1]; z = q[2];
-            if (fourth == 1) w = q[3];
+            if (stride == 4) {              // one 16-byte load per point (stride 4 scalar loads would conflict 4-way)
+                const float4 v = reinterpret_cast<const float4 *>(s_raw)[p];
+                x = v.x; y = v.y; z = v.z;
+                if (fourth == 1) w = v.w;
+            } else {
+                const float *q = s_raw + p * stride;
+                x = q[0]; y = q[1]; z = q[2];
+                if (fourth == 1) w = q[3];
+            }
             if (use_close && fabsf(x) < close_thr && fabsf(y) < close_thr) keep = false;
             apply_chain(s_chain, x, y, z);
             // `aggr_pc_points[2] > floor_thresh` of the reference's commented-out ground filter

@@ -39,6 +39,10 @@ struct OpRef {
 
 int op_size(int kind) { return kind == CM3D_OP_T ? 3 : (kind == CM3D_OP_R ? 9 : 12); }
 
+// nuScenes .bin rows are (x, y, z, intensity, ring index): nothing downstream reads the fifth column
+// (src/nuscenes/utils/pcd.py:246-257 keeps four), so it does not travel to the GPU.
+int64_t packed_stride(int64_t stride) { return stride == 5 ? 4 : stride; }
+
 void encode_chain(const OpRef *ops, int n, uint32_t *out)
 {
     memset(out, 0, CM3D_CHAIN_WORDS * 4);
@@ -164,7 +168,7 @@ int cm3d_pack_plan(const cm3d_pack_input *in, int64_t *plan)
             n_pts += n;
             if (n == 0) continue;
             n_tiles += (n + CM3D_TILE - 1) / CM3D_TILE;
-            raw += align4(n * in->sw_stride[si]);
+            raw += align4(n * packed_stride(in->sw_stride[si]));
         }
         const int I = in->fr_n_inst[f];
         if (I > CM3D_MAX_INST) return CM3D_ELIMIT;
@@ -213,12 +217,18 @@ int cm3d_pack_fill(const cm3d_pack_input *in, const int64_t *plan, float *raw, i
         const int I = in->fr_n_inst[f];
         const int t_begin = ti;
         for (int s = 0; s < in->fr_n_sweeps[f]; ++s, ++si) {
-            const int64_t n = in->sw_npts[si], stride = in->sw_stride[si];
+            const int64_t n = in->sw_npts[si], stride_in = in->sw_stride[si], stride = packed_stride(stride_in);
             const int64_t o = ro;
             int nt = 0;
             if (n > 0) {
                 nt = (int)((n + CM3D_TILE - 1) / CM3D_TILE);
-                memcpy(raw + o, reinterpret_cast<const float *>(in->sw_ptr[si]), (size_t)(n * stride) * 4);
+                const float *src = reinterpret_cast<const float *>(in->sw_ptr[si]);
+                if (stride == stride_in) {
+                    memcpy(raw + o, src, (size_t)(n * stride) * 4);
+                } else {
+                    float *dst = raw + o;
+                    for (int64_t k = 0; k < n; ++k) memcpy(dst + 4 * k, src + stride_in * k, 16);
+                }
                 for (int64_t k = n * stride; k < align4(n * stride); ++k) raw[o + k] = 0.0f;
                 ro += align4(n * stride);
             }
