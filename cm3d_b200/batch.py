@@ -449,6 +449,22 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
 
 # ------------------------------------------------------------------------------------------ native packer
 _KIND_CODE = {"T": 1, "R": 2, "A": 3}
+_PACK_PTR_FIELDS = ("fr_n_sweeps", "fr_n_cams", "fr_n_inst", "fr_fourth", "fr_min_pts", "fr_use_close", "fr_use_floor",
+                    "fr_close", "fr_min_dist", "fr_floor", "sw_ptr", "sw_npts", "sw_stride", "op_begin", "op_kind",
+                    "op_ptr", "cam_K", "in_cam", "in_W", "in_H", "in_counts_off", "counts")
+
+
+def _pack_input_type():
+    """ctypes mirror of `cm3d_pack_input` (include/cm3d_b200.h)."""
+    import ctypes
+
+    class PackInput(ctypes.Structure):
+        _fields_ = [("n_frames", ctypes.c_int32), ("n_sweeps", ctypes.c_int32), ("n_cams", ctypes.c_int32),
+                    ("n_inst", ctypes.c_int32)] + [(k, ctypes.c_void_p) for k in _PACK_PTR_FIELDS]
+    return PackInput
+
+
+_PackInput = None
 
 
 def _ptr_of(a: np.ndarray) -> int:
@@ -471,6 +487,8 @@ def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "Pi
             return pack_frames(frames, pin)
     if not any(f.n_instances for f in frames):
         return pack_frames(frames, pin)
+    if any(len(o) > 4 for f in frames for o in f.sweep_ops) or any(len(c.ops) > 4 for f in frames for c in f.cams):
+        return pack_frames(frames, pin)              # raises the chain-length error with its message
     lib = N.load()
 
     sw_ptr, sw_npts, sw_stride, op_begin, op_kind, op_ptr, cam_K = [], [], [], [0], [], [], []
@@ -514,17 +532,10 @@ def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "Pi
         sw_ptr=np.asarray(sw_ptr, np.uint64), sw_npts=i32(sw_npts), sw_stride=i32(sw_stride),
         op_begin=i32(op_begin), op_kind=i32(op_kind), op_ptr=np.asarray(op_ptr, np.uint64),
         cam_K=np.asarray(cam_K, np.uint64), in_cam=in_cam, in_W=in_W, in_H=in_H, in_counts_off=in_counts_off)
-    for f in frames:
-        if len(f.sweeps) and any(len(o) > 4 for o in f.sweep_ops):
-            return pack_frames(frames, pin)
-
-    class _In(ctypes.Structure):
-        _fields_ = [("n_frames", ctypes.c_int32), ("n_sweeps", ctypes.c_int32), ("n_cams", ctypes.c_int32),
-                    ("n_inst", ctypes.c_int32)] + [(k, ctypes.c_void_p) for k in (
-                        "fr_n_sweeps", "fr_n_cams", "fr_n_inst", "fr_fourth", "fr_min_pts", "fr_use_close", "fr_use_floor",
-                        "fr_close", "fr_min_dist", "fr_floor", "sw_ptr", "sw_npts", "sw_stride", "op_begin", "op_kind",
-                        "op_ptr", "cam_K", "in_cam", "in_W", "in_H", "in_counts_off", "counts")]
-    inp = _In(F, len(sw_ptr), len(cam_K), n_inst)
+    global _PackInput
+    if _PackInput is None:
+        _PackInput = _pack_input_type()
+    inp = _PackInput(F, len(sw_ptr), len(cam_K), n_inst)
     for k, a in arrs.items():
         setattr(inp, k, _ptr_of(a))
     inp.counts = ctypes.cast(ctypes.c_char_p(blob), ctypes.c_void_p).value
