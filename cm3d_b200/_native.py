@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CM3D_B200_LIB") or os.path.join(_HERE, "_lib", "libcm3d_b200.so")   # env: kernel experiments
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int

@@ -332,7 +332,7 @@ class Lifter:
             screen_min = torch.empty(5 * I, **i32) if screen else None
             sym_ws = torch.empty(5 * seg_cap, dtype=torch.float32, device=dev) if screen and not (self.screen_flags & 3) else None
             screen_stats = torch.zeros(1, **i32) if screen else None
-            item_pos = torch.empty(max_items, **i32)
+            item_pos = torch.empty(4 * max_items, **i32)     # item_info: {instance, q, o, m} per item
             self._call("medoid", "cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), _ptr(seg_point_idx),
                    _ptr(o("item_off")), _ptr(item_inst), I, max_items, _ptr(medoid_best), _ptr(col_sums),
                    _ptr(screen_sums), _ptr(screen_min), int(self.screen_min_pts) if screen else 0, int(self.screen_flags), _ptr(sym_ws),

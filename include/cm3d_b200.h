@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 9
+#define CM3D_ABI_VERSION 10
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
@@ -208,14 +208,15 @@ int cm3d_compact_segments(const float *xyzw, const int32_t *tile_cnt, const int3
  * instances, instances with
  * coordinates outside the fast square root's range and every call with col_sums take the all-exact
  * path.  screen_stats (optional, 1 word, zeroed by the caller): receives the number of verified
- * columns.  item_pos (optional scratch, max_items words): item -> schedule position table, so that
- * the blocks of the item-grid launches find their instance with one load instead of a search. */
+ * columns.  item_info (optional scratch, 4 * max_items words, 16-byte aligned): item -> {instance, index
+ * inside it, segment offset, segment length}, so that the blocks of the item-grid launches find their work
+ * with one 16-byte load instead of a search and three dependent loads. */
 int cm3d_medoid(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off,
                 const int32_t *seg_point_idx, const int32_t *item_off, const int32_t *item_inst,
                 int n_inst_total,
                 int max_items, unsigned long long *medoid_best, float *col_sums,
                 float *screen_sums, uint32_t *screen_min, int screen_min_pts, int screen_flags,
-                float *sym_ws, int32_t *screen_stats, int32_t *item_pos, int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
+                float *sym_ws, int32_t *screen_stats, int32_t *item_info, int32_t *medoid_local, int32_t *medoid_point_idx, float *centroid,
                 const int32_t *errflags, void *stream);
 #define CM3D_SCREEN_MIN_PTS 512   /* default screen_min_pts */
 

@@ -212,7 +212,7 @@ def _medoid_abi(pts_list, screen_min_pts, want_sums=False, screen_flags=0):
     smin = torch.zeros(5 * n, dtype=torch.int32, device=dev)
     ws = torch.zeros(5 * cap, dtype=torch.float32, device=dev)
     stats = torch.zeros(1, dtype=torch.int32, device=dev)
-    ipos = torch.zeros(int(item_off[-1]) + 3, dtype=torch.int32, device=dev) if screen_min_pts != 32 else None
+    ipos = torch.zeros(4 * (int(item_off[-1]) + 3), dtype=torch.int32, device=dev) if screen_min_pts != 32 else None
     ml = torch.zeros(n, dtype=torch.int32, device=dev)
     mp = torch.zeros(n, dtype=torch.int32, device=dev)
     cen = torch.zeros(4 * n, dtype=torch.float32, device=dev)

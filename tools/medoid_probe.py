@@ -48,7 +48,7 @@ def run_case(name, sizes, reps=3, centre=(1200.0, 950.0, 1.0), order_desc=False,
     smin = torch.zeros(5 * n, dtype=torch.int32, device=dev)
     ws = torch.zeros(5 * cap, dtype=torch.float32, device=dev)
     flags = int(os.environ.get("CM3D_SCREEN_FLAGS", "0"))
-    ipos = torch.zeros(int(item_off[-1]) + 1, dtype=torch.int32, device=dev)
+    ipos = torch.zeros(4 * (int(item_off[-1]) + 1), dtype=torch.int32, device=dev)
     screen = int(os.environ.get("CM3D_SCREEN_MIN_PTS", "512"))
 
     def launch():
