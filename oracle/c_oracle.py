@@ -115,6 +115,16 @@ def medoid(xyz_3m, want_sums=False):
     return (int(j), sums) if want_sums else int(j)
 
 
+def sqdist(xyz_3m):
+    """m x m matrix of the matmul formula's squared distances before the clamp (row i, column j)."""
+    L = lib()
+    x, y, z = (np.ascontiguousarray(xyz_3m[i], np.float32) for i in range(3))
+    m = x.shape[0]
+    out = np.empty((m, m), np.float32)
+    L.oracle_sqdist(_p(x, _F), _p(y, _F), _p(z, _F), ctypes.c_long(m), _p(out, _F))
+    return out
+
+
 def lift_frame_c(frame: FrameSpec, record_pix=True, do_medoid=True):
     aggr = aggregate(frame)
     n = aggr.shape[1]

@@ -279,3 +279,22 @@ long oracle_medoid(const float *x, const float *y, const float *z, long m, float
 {
     return oracle_medoid_mt(x, y, z, m, sums, 1);
 }
+
+/* The matmul formula's squared distance before the clamp, r(i, j) with row i of x1 and row j of x2 (the same
+ * chain as pair_dist above), as an m x m row-major matrix: tests of the symmetry conditions the CUDA screen
+ * relies on (cm3d_b200/csrc/medoid.cu: k_medoid_classify). */
+void oracle_sqdist(const float *x, const float *y, const float *z, long m, float *out)
+{
+    float *nrm = (float *)malloc(sizeof(float) * (size_t)(m > 0 ? m : 1));
+    for (long i = 0; i < m; i++) nrm[i] = (x[i] * x[i] + y[i] * y[i]) + z[i] * z[i];
+    for (long i = 0; i < m; i++)
+        for (long j = 0; j < m; j++) {
+            float r = (-2.0f * x[i]) * x[j];
+            r = fmaf(-2.0f * y[i], y[j], r);
+            r = fmaf(-2.0f * z[i], z[j], r);
+            r = fmaf(nrm[i], 1.0f, r);
+            r = fmaf(1.0f, nrm[j], r);
+            out[i * m + j] = r;
+        }
+    free(nrm);
+}

@@ -101,3 +101,57 @@ def test_obb_oracle_yaw_matches_live_scipy_on_proper_rotations():
             assert np.isfinite(O.yaw_of(R))
             improper += 1
     assert proper > 20 and improper > 20
+
+
+def _screen_groups(p):
+    """Python restatement of k_medoid_classify / k_medoid_permute (cm3d_b200/csrc/medoid.cu): None when the
+    instance is not eligible for a symmetric screen, else the group (0 lower binade, 1 its top sliver, 2 upper
+    binade) of every point; one binade -> all zeros."""
+    x, y, z = p.astype(np.float32)
+    n = (x * x + y * y) + z * z
+    bits = n.view(np.uint32)
+    e, mant = bits >> 23, bits & 0x7FFFFF
+    ext = np.array([np.ptp(x), np.ptp(y), np.ptp(z)], np.float32)
+    diag2 = np.float32(ext @ ext) * np.float32(1.001)
+    nmin, nmax = n.min(), n.max()
+    top_margin = (np.float32(nmax).view(np.uint32) & 0x7FFFFF) <= 0x7FFFE0
+    if not (nmin > 0 and top_margin and diag2 <= np.float32(0.25) * nmin):
+        return None
+    if e.min() == e.max():
+        return np.zeros(n.size, int)
+    if e.max() == e.min() + 1:
+        return np.where(e == e.min(), np.where(mant <= 0x7FFFF8, 0, 1), 2)
+    return None
+
+
+def test_squared_distance_matrix_is_symmetric_where_the_screen_assumes_it():
+    """The proof behind the CUDA medoid's symmetric screen, checked on the C oracle's fp32 arithmetic: inside a
+    group that k_medoid_classify declares symmetric, r(i, j) == r(j, i) bit for bit; across the groups it is
+    not in general (so the test can see an asymmetry when there is one)."""
+    from oracle import c_oracle as CO
+    rng = np.random.default_rng(3)
+    cases = []
+    for c, sg in (((1200.0, 950.0, 1.0), 3.0), ((420.0, 1900.0, -0.5), 6.0), ((1023.0, 1025.0, 0.0), 1.5), ((1024.0, 1024.0, 0.0), 1.5),
+                  ((35.0, 2.0, 15.0), 0.5), ((6.0, -1.0, 5.5), 0.15), ((0.9, 0.1, 0.2), 0.02), ((300.5, 300.5, 2.0), 8.0),
+                  ((724.0, 724.2, 0.3), 4.0), ((1448.0, 10.0, 0.0), 2.0), ((2000.0, 2000.0, 1.0), 10.0)):
+        for m in (300, 700):
+            cases.append((rng.normal(0, sg, (3, m)) + np.array(c)[:, None]).astype(np.float32))
+    n_sym = n_grouped = cross_asym = 0
+    for p in cases:
+        g = _screen_groups(p)
+        if g is None:
+            continue
+        r = CO.sqdist(p).view(np.uint32)
+        same = (g[:, None] == g[None, :]) & (g[:, None] != 1)
+        assert np.array_equal(r[same], r.T[same]), p.mean(1)
+        if g.max() == 0:
+            n_sym += 1
+        else:
+            n_grouped += 1
+            cross_asym += int((r != r.T)[~same].sum())
+    assert n_sym >= 8 and n_grouped >= 3 and cross_asym > 0
+    # and an instance that fails the conditions really is asymmetric (sensor frame, several binades)
+    p = (rng.normal(0, 2, (3, 400)) + np.float32(10.0)).astype(np.float32)
+    assert _screen_groups(p) is None
+    r = CO.sqdist(p).view(np.uint32)
+    assert (r != r.T).any()
