@@ -155,3 +155,32 @@ def test_squared_distance_matrix_is_symmetric_where_the_screen_assumes_it():
     assert _screen_groups(p) is None
     r = CO.sqdist(p).view(np.uint32)
     assert (r != r.T).any()
+
+
+def test_screen_error_bound_of_the_blocked_summation():
+    """The bound the CUDA screen's candidate threshold rests on (csrc/medoid.cu: screen_threshold): the screen's
+    summation order (16 rows -> a0, a 1024-row tile -> a1, tiles -> a2) over square roots that are one ulp off
+    is within (168 + M/1024 + M/4096) u of the reference's cascade sum, u = 2^-24.  Restated in numpy on the C
+    oracle's distances; what is observed stays far inside the bound."""
+    from oracle import c_oracle as CO
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for m, c, sg in ((700, (1200.0, 950.0, 1.0), 3.0), (2100, (420.0, 1900.0, -0.5), 5.0), (1500, (10.0, 1.0, 20.0), 2.0)):
+        p = (rng.normal(0, sg, (3, m)) + np.array(c)[:, None]).astype(np.float32)
+        _, ref = CO.medoid(p, want_sums=True)
+        d = np.sqrt(np.maximum(CO.sqdist(p), np.float32(0.0)))                 # rows i, columns j, correctly rounded
+        d1 = np.nextafter(d, np.float32(np.inf)) * (d > 0)                     # a root that is one ulp off everywhere
+        blk = np.zeros(m, np.float32)
+        for t0 in range(0, m, 1024):
+            a1 = np.zeros(m, np.float32)
+            for b in range(t0, min(m, t0 + 1024), 16):
+                a0 = np.zeros(m, np.float32)
+                for i in range(b, min(m, b + 16)):
+                    a0 += d1[i]
+                a1 += a0
+            blk += a1
+        bound = (168 + m // 1024 + m // 4096) * 2.0 ** -24
+        rel = float(np.max(np.abs(blk.astype(np.float64) - ref) / ref))
+        assert rel <= bound, (m, rel, bound)
+        worst = max(worst, rel / bound)
+    assert worst < 0.25
