@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CM3D_B200_LIB") or os.path.join(_HERE, "_lib", "libcm3d_b200.so")   # env: kernel experiments
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -30,7 +30,7 @@ PROTOTYPES = {
     "cm3d_compact_segments": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P],
     "cm3d_medoid": [_P, _L, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "cm3d_medoid_items": [_I, _I],
-    "cm3d_pca_obb": [_P, _L, _P, _I, _I, _P, _P, _P],
+    "cm3d_hull_obb": [_P, _L, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P],
     "cm3d_neighbor_filter": [_P, _L, _P, _I, _I, ctypes.c_float, _I, _P, _P, _P, _P],
     "cm3d_schedule_segments": [_P, _P, _I, _L, _P, _P, _P, _P, _P, _P],
     "cm3d_filter_segments": [_P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P],
@@ -41,7 +41,7 @@ PROTOTYPES = {
     "cm3d_pack_plan": [_P, _P],
     "cm3d_pack_fill": [_P, _P, _P, _P, _P, _P, _P, _P],
 }
-EXPORTS = ["cm3d_abi_version", "cm3d_error_string"] + list(PROTOTYPES)
+EXPORTS = ["cm3d_abi_version", "cm3d_error_string", "cm3d_hull_obb_ws_words"] + list(PROTOTYPES)
 
 _lib = None
 
@@ -63,6 +63,8 @@ def load():
     lib.cm3d_abi_version.restype = ctypes.c_int
     lib.cm3d_error_string.restype = ctypes.c_char_p
     lib.cm3d_error_string.argtypes = [ctypes.c_int]
+    lib.cm3d_hull_obb_ws_words.restype = ctypes.c_int64
+    lib.cm3d_hull_obb_ws_words.argtypes = [ctypes.c_int64]
     v = lib.cm3d_abi_version()
     if v != ABI_VERSION:
         raise Cm3dError(f"libcm3d_b200.so has ABI {v}, python side expects {ABI_VERSION}: rebuild")

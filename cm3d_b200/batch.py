@@ -82,7 +82,8 @@ def cull_planes(cam, W: int, H: int, min_dist32, tref):
         return _OFF_PLANES.copy(), flags
     tref = np.asarray(tref, np.float64)
     first_T = len(cam.ops) and cam.ops[0][0] == "T"
-    t0 = tref + np.asarray(cam.ops[0][1], np.float64) if first_T else tref
+    # q = p + tref, so a camera whose first op is T(t_c) sees q + (t_c - tref): the residual translation
+    t0 = np.asarray(cam.ops[0][1], np.float64) - tref if first_T else tref
     tau += abs(float(t0[0])) + abs(float(t0[1])) + abs(float(t0[2]))
     c2 = c - M @ tref                                   # p = q - tref
     abc = np.array([[0.0, 0.0, 1.0],                                  # z > min_dist
@@ -132,7 +133,7 @@ def cull_planes_many(cams, sizes, min_dist32, tref):
                 tau = tau + np.abs(m[:, :, 3]).sum(1)
     tref = np.asarray(tref, np.float64)
     if kinds and kinds[0] == "T":
-        t0 = tref + np.stack([np.asarray(cam.ops[0][1], np.float64) for cam in cams])
+        t0 = np.stack([np.asarray(cam.ops[0][1], np.float64) for cam in cams]) - tref      # residual, see cull_planes
         tau = tau + np.abs(t0).sum(1)
     else:
         tau = tau + np.abs(tref).sum()

@@ -1,19 +1,36 @@
-// KITTI orientation: principal-axes box of an instance's points and the yaw the reference derives
-// from it (src/kitti/2d_to_3d.py:855-876 `get_depth_bbox`, :1524 `as_euler('zyx')[0]`).
+// KITTI orientation: open3d's oriented bounding box of an instance's points and the yaw the reference
+// derives from it (src/kitti/2d_to_3d.py:855-876 `get_depth_bbox`, :1481-1484 fallback, :1524
+// `as_euler('zyx')[0]`).
 //
-// PARITY UNPINNED.  The reference calls open3d 0.15.2 `get_oriented_bounding_box()`, which is not
-// in the reference tree (un-vendored pip dependency) and not installed here; upstream it is the PCA
-// of the convex-hull vertices.  This kernel computes the PCA of the MEMBER POINTS themselves (no
-// hull), with this documented convention, and is graded against oracle/obb_oracle.py only:
-//   mean, covariance (population, fp64) -> symmetric eigen-decomposition (cyclic Jacobi, fp64)
-//   -> columns sorted by descending eigenvalue -> each of the first two columns flipped so that
-//   its largest-magnitude component is positive -> third column = col0 x col1
-//   -> extent / centre from the min/max of R^T (p - mean)
+// The reference calls open3d 0.15.2 `get_oriented_bounding_box()` (un-vendored pip dependency, absent
+// here).  Its published algorithm (OrientedBoundingBox::CreateFromPoints) is restated in
+// oracle/obb_oracle.py and implemented here:
+//   convex hull (Qhull)  ->  k_hull_obb: per instance, the set of HULL VERTICES by gift wrapping
+//   mean, covariance of the hull vertices (E[xx^T] - E[x]E[x]^T, fp64) -> symmetric eigen-decomposition
+//   (cyclic Jacobi, fp64) -> columns sorted by descending eigenvalue, col2 = col0 x col1
+//   -> extent / centre from the min/max of R^T (v - mean) over the hull vertices
 //   -> the reference's axis shuffle: axes sorted by axis-aligned size ascending,
 //      wlh = [extent[idx x], extent[idx y], extent[idx z]], R' = [R[:,idx z], R[:,idx y], R[:,idx x]]
 //   -> yaw = scipy 1.11.4 `Rotation.from_matrix(R').as_euler('zyx')[0]` restated (quaternion by the
 //      largest of m00/m11/m22/trace, no determinant check - R' is left-handed for odd shuffles)
-// One block per instance; reads the gathered segment (SoA) three times from L2.
+// PARITY UNPINNED against the open3d binary in one respect: the SIGN of Eigen's eigenvectors is
+// implementation defined; here (and in the oracle) each of the first two columns is flipped so that its
+// largest-magnitude component is positive.  A cloud Qhull rejects (flat: collinear / coplanar points)
+// makes the reference's bare `except` substitute centre = first point, extent 1, R = identity; the
+// kernel does the same when its hull is flat (exact test) or its wrapping does not close.
+//
+// Gift wrapping (one block of 1024 threads per instance, fp64 on the fp32 coordinates, differences
+// against the edge origin are exact): start from the lexicographically smallest point a, the next
+// point b of the 2-D hull of the xy projection (so the vertical plane through ab supports the cloud),
+// and wrap around directed edges: the face (s,t,p) across edge (s,t) is the p for which no point q
+// has det[t-s, p-s, q-s] > 0 - a tournament (thread-local, then warp shuffles, then across warps)
+// whose pairwise comparison is always evaluated with the lower point index first, so every lane
+// reaches the same decision.  Faces go to a per-instance list in the workspace; a directed edge is
+// open while no listed face contains it (block-wide scan of the list, a few hundred to a few thousand
+// faces).  O(faces x points) determinant evaluations per instance: h ~ 10^2..10^3 of M <= ~2*10^4.
+// Exact ties (four coplanar hull points, duplicates) take the candidate on the far side of the old
+// face, then the one farther from the edge, then the lower index; Qhull's own tolerance-based facet
+// merging is NOT reproduced (it only matters for points within ~1e-13 m of a facet plane).
 #include "common.cuh"
 
 namespace cm3d {
@@ -75,12 +92,253 @@ __device__ void jacobi3(double a[3][3], double v[3][3])
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_pca_obb(const float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *__restrict__ seg_off, int min_pts,
-          float *__restrict__ obb, const int32_t *__restrict__ errflags)
+// ------------------------------------------------------------------------------------------ hull vertices
+constexpr int kHullThreads = 1024;
+
+struct HullPts {
+    const float *x, *y, *z;
+    int m;
+    __device__ __forceinline__ void get(int r, double &px, double &py, double &pz) const
+    {
+        px = (double)__ldg(x + r); py = (double)__ldg(y + r); pz = (double)__ldg(z + r);
+    }
+};
+
+// Directed edge being wrapped: origin S, direction e = T - S, and the third vertex of the face the
+// edge came from, relative to S (wz; the tie rule for coplanar neighbours needs its side).
+struct HullEdge {
+    double sx, sy, sz, ex, ey, ez, zx, zy, zz;
+};
+
+// Should candidate b replace candidate a as third vertex of the face on edge E?  Evaluated on
+// (lower index, higher index) whatever the argument order, so both sides of a shuffle agree.
+__device__ bool hull_beats(const HullPts &P, const HullEdge &E, int a, int b)
 {
-    __shared__ double s_red[8];
-    __shared__ float s_redf[8];
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    double lx, ly, lz, hx, hy, hz;
+    P.get(lo, lx, ly, lz);
+    P.get(hi, hx, hy, hz);
+    lx -= E.sx; ly -= E.sy; lz -= E.sz;
+    hx -= E.sx; hy -= E.sy; hz -= E.sz;
+    const double nlx = E.ey * lz - E.ez * ly, nly = E.ez * lx - E.ex * lz, nlz = E.ex * ly - E.ey * lx;   // e x w_lo
+    const double d = nlx * hx + nly * hy + nlz * hz;          // > 0: hi lies outside the plane (S, T, lo)
+    if (d > 0.0) return b == hi;
+    if (d < 0.0) return b == lo;
+    const double nhx = E.ey * hz - E.ez * hy, nhy = E.ez * hx - E.ex * hz, nhz = E.ex * hy - E.ey * hx;
+    const double nnl = nlx * nlx + nly * nly + nlz * nlz, nnh = nhx * nhx + nhy * nhy + nhz * nhz;
+    if (nnh == 0.0) return b == lo && nnl > 0.0;              // a point on the edge's line is never a third vertex
+    if (nnl == 0.0) return b == hi;
+    if (nlx * nhx + nly * nhy + nlz * nhz < 0.0) {            // coplanar, on opposite sides of the edge:
+        const double nzx = E.ey * E.zz - E.ez * E.zy, nzy = E.ez * E.zx - E.ex * E.zz, nzz = E.ex * E.zy - E.ey * E.zx;
+        const double side_lo = nlx * nzx + nly * nzy + nlz * nzz;       // the far side of the old face wins
+        return side_lo < 0.0 ? b == lo : b == hi;
+    }
+    if (nnh > nnl) return b == hi;                             // same side: farther from the edge, then lower index
+    return b == lo;
+}
+
+// p such that no point lies outside the plane (S, T, p); -1 when every point is on the edge's line.
+__device__ int hull_wrap(const HullPts &P, const HullEdge &E, int s, int t, int *s_cand)
+{
+    int best = -1;
+    for (int r = threadIdx.x; r < P.m; r += blockDim.x) {
+        if (r == s || r == t) continue;
+        if (best < 0) {
+            double wx, wy, wz;
+            P.get(r, wx, wy, wz);
+            wx -= E.sx; wy -= E.sy; wz -= E.sz;
+            const double nx = E.ey * wz - E.ez * wy, ny = E.ez * wx - E.ex * wz, nz = E.ex * wy - E.ey * wx;
+            if (nx * nx + ny * ny + nz * nz > 0.0) best = r;
+        } else if (hull_beats(P, E, best, r)) {
+            best = r;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other >= 0 && other != best && (best < 0 || hull_beats(P, E, best, other))) best = other;
+    }
+    __syncthreads();
+    if (lane_id() == 0) s_cand[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int b2 = threadIdx.x < (blockDim.x >> 5) ? s_cand[threadIdx.x] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int other = __shfl_xor_sync(0xffffffffu, b2, o);
+            if (other >= 0 && other != b2 && (b2 < 0 || hull_beats(P, E, b2, other))) b2 = other;
+        }
+        if (threadIdx.x == 0) s_cand[32] = b2;
+    }
+    __syncthreads();
+    return s_cand[32];
+}
+
+// lexicographic (x, y, z, index) minimum over the block
+__device__ int hull_lexmin(const HullPts &P, int *s_cand)
+{
+    auto less = [&](int a, int b) {
+        double ax, ay, az, bx, by, bz;
+        P.get(a, ax, ay, az);
+        P.get(b, bx, by, bz);
+        if (ax != bx) return ax < bx;
+        if (ay != by) return ay < by;
+        if (az != bz) return az < bz;
+        return a < b;
+    };
+    int best = -1;
+    for (int r = threadIdx.x; r < P.m; r += blockDim.x)
+        if (best < 0 || less(r, best)) best = r;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other >= 0 && (best < 0 || less(other, best))) best = other;
+    }
+    __syncthreads();
+    if (lane_id() == 0) s_cand[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b2 = -1;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+            if (s_cand[w] >= 0 && (b2 < 0 || less(s_cand[w], b2))) b2 = s_cand[w];
+        s_cand[32] = b2;
+    }
+    __syncthreads();
+    return s_cand[32];
+}
+
+// next vertex after a on the counter-clockwise 2-D hull of the xy projection: every other point is
+// to the left of a -> b (ties: the farther one, then the lower index); -1 when all share a's (x, y).
+__device__ int hull_next2d(const HullPts &P, int a, int *s_cand)
+{
+    double ax, ay, az;
+    P.get(a, ax, ay, az);
+    auto beats = [&](int p, int q) {       // should q replace p?
+        const int lo = p < q ? p : q, hi = p < q ? q : p;
+        double lx, ly, lz, hx, hy, hz;
+        P.get(lo, lx, ly, lz);
+        P.get(hi, hx, hy, hz);
+        lx -= ax; ly -= ay; hx -= ax; hy -= ay;
+        const double c = lx * hy - ly * hx;            // < 0: hi is to the right of a -> lo
+        if (c < 0.0) return q == hi;
+        if (c > 0.0) return q == lo;
+        const double dl = lx * lx + ly * ly, dh = hx * hx + hy * hy;
+        if (dh > dl) return q == hi;
+        return q == lo;
+    };
+    auto valid = [&](int r) {
+        double x, y, z;
+        P.get(r, x, y, z);
+        return r != a && (x != ax || y != ay);
+    };
+    int best = -1;
+    for (int r = threadIdx.x; r < P.m; r += blockDim.x) {
+        if (!valid(r)) continue;
+        if (best < 0 || beats(best, r)) best = r;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other >= 0 && other != best && (best < 0 || beats(best, other))) best = other;
+    }
+    __syncthreads();
+    if (lane_id() == 0) s_cand[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b2 = -1;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+            if (s_cand[w] >= 0 && s_cand[w] != b2 && (b2 < 0 || beats(b2, s_cand[w]))) b2 = s_cand[w];
+        s_cand[32] = b2;
+    }
+    __syncthreads();
+    return s_cand[32];
+}
+
+// is the directed edge (s, t) part of a listed face?
+__device__ bool hull_edge_listed(const int32_t *faces, int n_faces, int s, int t)
+{
+    int found = 0;
+    for (int f = threadIdx.x; f < n_faces; f += blockDim.x) {
+        const int a = faces[3 * f], b = faces[3 * f + 1], c = faces[3 * f + 2];
+        found |= (a == s && b == t) || (b == s && c == t) || (c == s && a == t);
+    }
+    return __syncthreads_or(found) != 0;
+}
+
+// Flags the convex-hull vertices of the block's instance in vflag[0..m).  Returns the number of faces
+// (>= 4), or 0 when the cloud is flat (collinear / coplanar) or the wrapping did not close.
+__device__ int hull_vertices(const HullPts &P, int32_t *faces, int face_cap, uint8_t *vflag, int *s_cand)
+{
+    for (int r = threadIdx.x; r < P.m; r += blockDim.x) vflag[r] = 0;
+    const int a = hull_lexmin(P, s_cand);
+    const int b = hull_next2d(P, a, s_cand);
+    if (b < 0) return 0;
+    double ax, ay, az, bx, by, bz;
+    P.get(a, ax, ay, az);
+    P.get(b, bx, by, bz);
+    HullEdge E;
+    // first face: across the reversed edge (b, a) of the virtual vertical face (a, b, a + (0,0,1))
+    E.sx = bx; E.sy = by; E.sz = bz;
+    E.ex = ax - bx; E.ey = ay - by; E.ez = az - bz;
+    E.zx = E.ex; E.zy = E.ey; E.zz = E.ez + 1.0;
+    const int p0 = hull_wrap(P, E, b, a, s_cand);
+    if (p0 < 0) return 0;
+    {   // flat cloud: every point in the plane of the first face (exact test)
+        double px, py, pz;
+        P.get(p0, px, py, pz);
+        px -= bx; py -= by; pz -= bz;
+        const double nx = E.ey * pz - E.ez * py, ny = E.ez * px - E.ex * pz, nz = E.ex * py - E.ey * px;
+        int off = 0;
+        for (int r = threadIdx.x; r < P.m; r += blockDim.x) {
+            double qx, qy, qz;
+            P.get(r, qx, qy, qz);
+            off |= (nx * (qx - bx) + ny * (qy - by) + nz * (qz - bz)) != 0.0;
+        }
+        if (!__syncthreads_or(off)) return 0;
+    }
+    int n_faces = 1;
+    if (threadIdx.x == 0) {
+        faces[0] = b; faces[1] = a; faces[2] = p0;
+        vflag[a] = vflag[b] = vflag[p0] = 1;
+    }
+    __syncthreads();
+    for (int k = 0; k < n_faces; ++k) {
+        const int fx = faces[3 * k], fy = faces[3 * k + 1], fz = faces[3 * k + 2];
+        for (int j = 0; j < 3; ++j) {
+            const int u = j == 0 ? fx : (j == 1 ? fy : fz);
+            const int v = j == 0 ? fy : (j == 1 ? fz : fx);
+            const int w = j == 0 ? fz : (j == 1 ? fx : fy);
+            if (hull_edge_listed(faces, n_faces, v, u)) continue;          // the neighbour across (u, v) exists
+            double vx, vy, vz, ux, uy, uz, wx, wy, wz;
+            P.get(v, vx, vy, vz);
+            P.get(u, ux, uy, uz);
+            P.get(w, wx, wy, wz);
+            E.sx = vx; E.sy = vy; E.sz = vz;
+            E.ex = ux - vx; E.ey = uy - vy; E.ez = uz - vz;
+            E.zx = wx - vx; E.zy = wy - vy; E.zz = wz - vz;
+            const int p = hull_wrap(P, E, v, u, s_cand);
+            if (p < 0 || p == w || n_faces >= face_cap) return 0;
+            if (threadIdx.x == 0) {
+                faces[3 * n_faces] = v; faces[3 * n_faces + 1] = u; faces[3 * n_faces + 2] = p;
+                vflag[p] = 1;
+            }
+            ++n_faces;
+            __syncthreads();
+        }
+    }
+    return n_faces;
+}
+
+// ------------------------------------------------------------------------------------------ the box
+// mode 0: hull vertices (open3d); mode 1: all member points (round 1's estimator, kept for comparison)
+__global__ void __launch_bounds__(kHullThreads)
+k_hull_obb(const float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *__restrict__ seg_off, int min_pts, int mode,
+           int32_t *__restrict__ hull_ws, float *__restrict__ obb, int32_t *__restrict__ hull_info,
+           const int32_t *__restrict__ errflags)
+{
+    __shared__ double s_red[32];
+    __shared__ float s_redf[32];
+    __shared__ int s_cand[33];
     __shared__ double s_R[3][3];
     __shared__ double s_mean[3];
     const int i = blockIdx.x;
@@ -89,30 +347,50 @@ k_pca_obb(const float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *__
     const int o = seg_off[i], m = seg_off[i + 1] - o;
     if (errflags[CM3D_ERR_SEG_OVERFLOW] != 0 || m < min_pts || m < 1) {
         if (threadIdx.x < 16) out[threadIdx.x] = nanv;
+        if (threadIdx.x == 0 && hull_info) hull_info[i] = 0;
         return;
     }
     const float *sx = seg_xyzw + o, *sy = seg_xyzw + seg_cap + o, *sz = seg_xyzw + 2 * seg_cap + o;
-    // pass 1: mean and axis-aligned min/max
-    double ax = 0, ay = 0, az = 0;
+    uint8_t *vflag = reinterpret_cast<uint8_t *>(hull_ws + 6 * seg_cap) + o;
+    int n_faces = -1;
+    if (mode == 0) {
+        HullPts P{sx, sy, sz, m};
+        n_faces = hull_vertices(P, hull_ws + 6 * (int64_t)o, 2 * m, vflag, s_cand);
+        __syncthreads();
+        if (n_faces == 0) {       // kitti:1483-1484: bbox = [pts3d[0], [1,1,1], identity] -> yaw 0
+            if (threadIdx.x == 0) {
+                out[0] = 0.0f; out[1] = sx[0]; out[2] = sy[0]; out[3] = sz[0];
+                out[4] = out[5] = out[6] = 1.0f;
+                for (int k = 0; k < 9; ++k) out[7 + k] = (k % 4 == 0) ? 1.0f : 0.0f;
+                if (hull_info) hull_info[i] = -1;
+            }
+            return;
+        }
+    }
+    // pass 1: first and second moments of the selected points, axis-aligned size of ALL points (kitti:863-865)
+    double a1[3] = {0, 0, 0}, a2[6] = {0, 0, 0, 0, 0, 0};
+    int cnt = 0;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int r = threadIdx.x; r < m; r += blockDim.x) {
         const float x = sx[r], y = sy[r], z = sz[r];
-        ax += x; ay += y; az += z;
         lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x);
         lo[1] = fminf(lo[1], y); hi[1] = fmaxf(hi[1], y);
         lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
+        if (mode == 0 && !vflag[r]) continue;
+        const double dx = x, dy = y, dz = z;
+        ++cnt;
+        a1[0] += dx; a1[1] += dy; a1[2] += dz;
+        a2[0] += dx * dx; a2[1] += dx * dy; a2[2] += dx * dz; a2[3] += dy * dy; a2[4] += dy * dz; a2[5] += dz * dz;
     }
-    const double mx = block_sum(ax, s_red) / m, my = block_sum(ay, s_red) / m, mz = block_sum(az, s_red) / m;
+    const double n = block_sum((double)cnt, s_red);
+    const double mx = block_sum(a1[0], s_red) / n, my = block_sum(a1[1], s_red) / n, mz = block_sum(a1[2], s_red) / n;
+    double c[6];
+    for (int k = 0; k < 6; ++k) c[k] = block_sum(a2[k], s_red) / n;
+    c[0] -= mx * mx; c[1] -= mx * my; c[2] -= mx * mz; c[3] -= my * my; c[4] -= my * mz; c[5] -= mz * mz;
     float size[3];
     for (int k = 0; k < 3; ++k) size[k] = -block_min(-hi[k], s_redf) - block_min(lo[k], s_redf);
-    // pass 2: covariance
-    double c[6] = {0, 0, 0, 0, 0, 0};
-    for (int r = threadIdx.x; r < m; r += blockDim.x) {
-        const double dx = sx[r] - mx, dy = sy[r] - my, dz = sz[r] - mz;
-        c[0] += dx * dx; c[1] += dx * dy; c[2] += dx * dz; c[3] += dy * dy; c[4] += dy * dz; c[5] += dz * dz;
-    }
-    for (int k = 0; k < 6; ++k) c[k] = block_sum(c[k], s_red) / m;
     if (threadIdx.x == 0) {
+        if (hull_info) hull_info[i] = mode == 0 ? (n_faces == 2 * (int)n - 4 ? (int)n : -(int)n - 1) : (int)n;
         double a[3][3] = {{c[0], c[1], c[2]}, {c[1], c[3], c[4]}, {c[2], c[4], c[5]}}, v[3][3];
         jacobi3(a, v);
         int ord[3] = {0, 1, 2};                       // descending eigenvalue, stable
@@ -122,12 +400,12 @@ k_pca_obb(const float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *__
         double R[3][3];
         for (int col = 0; col < 2; ++col) {
             double e[3] = {v[0][ord[col]], v[1][ord[col]], v[2][ord[col]]};
-            const double n = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+            const double nn = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
             int big = 0;
             if (fabs(e[1]) > fabs(e[big])) big = 1;
             if (fabs(e[2]) > fabs(e[big])) big = 2;
             const double sgn = e[big] < 0.0 ? -1.0 : 1.0;
-            for (int k = 0; k < 3; ++k) R[k][col] = sgn * e[k] / n;
+            for (int k = 0; k < 3; ++k) R[k][col] = sgn * e[k] / nn;
         }
         R[0][2] = R[1][0] * R[2][1] - R[2][0] * R[1][1];
         R[1][2] = R[2][0] * R[0][1] - R[0][0] * R[2][1];
@@ -137,9 +415,10 @@ k_pca_obb(const float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *__
         s_mean[0] = mx; s_mean[1] = my; s_mean[2] = mz;
     }
     __syncthreads();
-    // pass 3: extent / centre in the principal frame
+    // pass 2: extent / centre in the principal frame
     float plo[3] = {INFINITY, INFINITY, INFINITY}, phi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int r = threadIdx.x; r < m; r += blockDim.x) {
+        if (mode == 0 && !vflag[r]) continue;
         const double dx = sx[r] - s_mean[0], dy = sy[r] - s_mean[1], dz = sz[r] - s_mean[2];
         for (int k = 0; k < 3; ++k) {
             const float q = (float)(s_R[0][k] * dx + s_R[1][k] * dy + s_R[2][k] * dz);
@@ -205,13 +484,18 @@ k_pca_obb(const float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *__
 
 using namespace cm3d;
 
-extern "C" int cm3d_pca_obb(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
-                            int min_pts, float *obb, const int32_t *errflags, void *stream)
+extern "C" int64_t cm3d_hull_obb_ws_words(int64_t seg_cap) { return 6 * seg_cap + (seg_cap + 3) / 4 + 4; }
+
+extern "C" int cm3d_hull_obb(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
+                             int min_pts, int mode, int32_t *hull_ws, int64_t hull_ws_words, float *obb,
+                             int32_t *hull_info, const int32_t *errflags, void *stream)
 {
-    if (n_inst_total < 0 || seg_cap < 0) return CM3D_EINVAL;
+    if (n_inst_total < 0 || seg_cap < 0 || (mode != 0 && mode != 1)) return CM3D_EINVAL;
     if (n_inst_total == 0) return CM3D_OK;
     if (!seg_xyzw || !seg_off || !obb || !errflags) return CM3D_EINVAL;
-    k_pca_obb<<<n_inst_total, 256, 0, (cudaStream_t)stream>>>(seg_xyzw, seg_cap, seg_off, min_pts, obb, errflags);
+    if (mode == 0 && (!hull_ws || hull_ws_words < cm3d_hull_obb_ws_words(seg_cap))) return CM3D_EINVAL;
+    k_hull_obb<<<n_inst_total, kHullThreads, 0, (cudaStream_t)stream>>>(seg_xyzw, seg_cap, seg_off, min_pts, mode, hull_ws,
+                                                                        obb, hull_info, errflags);
     CM3D_LAUNCH_CHECK();
     return CM3D_OK;
 }

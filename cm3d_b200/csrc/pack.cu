@@ -118,7 +118,7 @@ int cull_planes(const OpRef *ops, int n_ops, const float *K32, int W, int H, flo
     if (!ok || !bottom_ok || !finite) return switch_off();
     double tref[3] = {(double)tref32[0], (double)tref32[1], (double)tref32[2]};
     if (n_ops && ops[0].kind == CM3D_OP_T)
-        tau += fabs(tref[0] + (double)ops[0].m[0]) + fabs(tref[1] + (double)ops[0].m[1]) + fabs(tref[2] + (double)ops[0].m[2]);
+        tau += fabs((double)ops[0].m[0] - tref[0]) + fabs((double)ops[0].m[1] - tref[1]) + fabs((double)ops[0].m[2] - tref[2]);   // residual t_c - tref
     else
         tau += fabs(tref[0]) + fabs(tref[1]) + fabs(tref[2]);
     double c2[3];

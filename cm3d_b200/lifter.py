@@ -159,6 +159,8 @@ class Lifter:
         self.last_screen_modes = None          # device int32[3 I]: mode (0 exact, 1 all pairs, 2 symmetric, 3 grouped
         #                                        symmetric) | points in group 0 | points in the sliver group (mode 3)
         self.timing = None          # dict label -> [(start_event, end_event)] when bench.py profiles
+        self.obb_mode = 0           # KITTI box: 0 = hull vertices (open3d's algorithm), 1 = all member points (diagnostics)
+        self.last_hull_info = None  # device int32[I]: hull vertex count per instance (-1: flat cloud -> the reference's fallback box)
 
     def _call(self, label: str, name: str, *args):
         """One C-ABI call; with `self.timing` set, bracketed by CUDA events on the launch stream."""
@@ -342,15 +344,19 @@ class Lifter:
             self.launches += (6 if self.screen_flags & 1 else (8 if self.screen_flags & 2 else 9)) if screen else 3
         self.last_screen_stats = screen_stats
         self.last_screen_modes = screen_min[I:4 * I] if (do_medoid and I and screen_min is not None) else None
-        # ---- KITTI: principal-axes box + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479)
-        obb = None
+        # ---- KITTI: open3d's box of the hull vertices + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479)
+        obb = hull_info = None
         if want_obb is None:
             want_obb = pb.any_kitti
         if want_obb and I:
             obb = torch.empty(I * 16, dtype=torch.float32, device=dev)
-            self._call("pca_obb", "cm3d_pca_obb", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, 4, _ptr(obb),
-                       _ptr(o("errflags")), st)
+            hull_info = torch.empty(I, **i32)
+            ws_words = int(N.load().cm3d_hull_obb_ws_words(seg_cap)) if self.obb_mode == 0 else 1
+            hull_ws = torch.empty(ws_words, **i32)
+            self._call("hull_obb", "cm3d_hull_obb", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, 4, int(self.obb_mode),
+                       _ptr(hull_ws), ws_words, _ptr(obb), _ptr(hull_info), _ptr(o("errflags")), st)
             self.launches += 1
+        self.last_hull_info = hull_info
         box = None
         if box_search and I:
             kitti_flags = {f == "kitti" for f in pb.frame_datasets}

@@ -30,8 +30,14 @@ def init_distributed():
 
 
 def stage_device(cfg_device: str, world: int, local_rank: int) -> str:
-    """One process per GPU: under torchrun rank r lifts on cuda:<LOCAL_RANK>, else on the script's DEVICE."""
-    return f"cuda:{local_rank}" if world > 1 else cfg_device
+    """One process per GPU: under torchrun rank r lifts on cuda:<LOCAL_RANK>, else on the script's DEVICE.
+    With fewer visible GPUs than local ranks the ranks share them round-robin (correct, just not
+    faster): that is how the sharded path is exercised on a one-GPU box."""
+    if world <= 1:
+        return cfg_device
+    import torch
+    n = torch.cuda.device_count()
+    return f"cuda:{local_rank % n}" if n else f"cuda:{local_rank}"
 
 
 def shard_indices(n: int, rank: int, world: int, mode: str = "interleaved") -> List[int]:

@@ -194,12 +194,17 @@ def run(cfg, scenes: Iterable, points_fn: Optional[Callable] = None, lifter=None
         def frames():
             for frame_num, frame in enumerate(scene_frames):
                 t0 = time.time()
+                if frame_num == 0:
+                    # the reference takes the lanes inside its `try` (waymo:459-468), so a scene whose frame 0 has
+                    # no mask files dies later with a NameError / stale lanes; here frame 0's map is read either way
+                    lanes[0] = lanes_of_frame(frame)
                 try:
                     masks, data = load_frame_masks(cfg.INPUT_DIR, scene_name, frame_num)
                 except FileNotFoundError:
                     continue                                             # waymo:453-455
-                if frame_num == 0:
-                    lanes[0] = lanes_of_frame(frame)
+                for label in data["labels"]:                             # waymo:1060-1061 raises in pass 2, after all the
+                    if B.NUSC_TO_WAYMO.get(B.get_detection_name(label), "") not in WP.TYPE_BY_NAME:     # lifting: fail early
+                        raise ValueError(f"{scene_name} frame {frame_num}: label {label!r} has no Waymo type")
                 spec = frame_spec(frame, masks, data, cfg, points_fn)
                 kept.append((frame, data))
                 timer["io"] += time.time() - t0

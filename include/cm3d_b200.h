@@ -16,7 +16,7 @@
  *   cm3d_scan_segments      (no reference counterpart: sizes of the boolean-index results)
  *   cm3d_compact_segments   src/nuscenes/2d_to_3d.py:617-620 (track_points, gather)
  *   cm3d_medoid             src/nuscenes/2d_to_3d.py:116-119,641-663 (cdist medoid, centroid)
- *   cm3d_pca_obb            src/kitti/2d_to_3d.py:855-876,1524 (open3d OBB -> yaw; parity unpinned)
+ *   cm3d_hull_obb           src/kitti/2d_to_3d.py:855-876,1481-1484,1524 (open3d OBB of the hull vertices -> yaw)
  *   cm3d_nearest_lane       src/nuscenes/2d_to_3d.py:277-302 (closest lane point per centroid)
  *
  * Conventions: every pointer is a DEVICE pointer; the caller (PyTorch) owns and
@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 10
+#define CM3D_ABI_VERSION 11
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
@@ -226,12 +226,19 @@ int cm3d_medoid_items(int m, int min_pts);
 
 /* ---- KITTI orientation (PARITY UNPINNED: open3d is not in the reference tree) ------------------ */
 
-/* Principal-axes box of every instance with at least min_pts points and the reference's yaw
+/* open3d's oriented bounding box of every instance with at least min_pts points and the reference's yaw
  * (src/kitti/2d_to_3d.py:855-876,1524): obb[16*i..] = yaw, centre xyz, wlh (after the reference's
- * axis shuffle), R' row-major (9 floats); NaN for skipped instances.  PCA of the member points,
- * conventions in csrc/obb.cu. */
-int cm3d_pca_obb(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
-                 int min_pts, float *obb, const int32_t *errflags, void *stream);
+ * axis shuffle), R' row-major (9 floats); NaN for skipped instances.  mode 0 = open3d 0.15's published
+ * algorithm: PCA of the CONVEX-HULL VERTICES (found on the GPU by gift wrapping, csrc/obb.cu); a flat
+ * cloud gets the reference's fallback box (first point, extent 1, identity -> yaw 0, kitti:1483-1484).
+ * mode 1 = PCA of all member points (round 1's estimator; diagnostics only).  hull_ws: scratch of
+ * cm3d_hull_obb_ws_words(seg_cap) int32 words (mode 0).  hull_info (optional, n_inst_total ints):
+ * hull vertex count; -1 = flat / fallback; -(count+1) = wrapping closed with an inconsistent face
+ * count (exactly degenerate input); 0 = skipped. */
+int64_t cm3d_hull_obb_ws_words(int64_t seg_cap);
+int cm3d_hull_obb(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
+                  int min_pts, int mode, int32_t *hull_ws, int64_t hull_ws_words, float *obb,
+                  int32_t *hull_info, const int32_t *errflags, void *stream);
 
 /* ---- default-off extensions (north star (3)/(4); never executed by the reference: PARITY UNPINNED) ---- */
 

@@ -11,8 +11,27 @@ import subprocess
 
 import numpy as np
 
-from cm3d_b200.frames import FOURTH_NONE, FrameSpec, encode_chain
-from cm3d_b200.rle import rle_counts_to_runs
+from oracle.coco_rle import counts_to_runs
+
+FOURTH_NONE = 0
+FrameSpec = object      # duck-typed (see oracle/ref_lift.py)
+_OP_KIND = {"T": 1, "R": 2, "A": 3}     # op codes of lift_oracle.c: 16 words per op = kind, 12 floats, 3 pad
+
+
+def encode_chain(ops):
+    """A transform chain [("R"|"T"|"A", matrix), ...] as the 4 x 16 words lift_oracle.c reads."""
+    if len(ops) > 4:
+        raise ValueError("chain longer than 4 ops")
+    out = np.zeros(64, dtype=np.uint32)
+    for k, (kind, m) in enumerate(ops):
+        out[16 * k] = _OP_KIND[kind]
+        flat = np.ascontiguousarray(m, dtype=np.float32).reshape(-1)
+        out[16 * k + 1: 16 * k + 1 + flat.size] = flat.view(np.uint32)
+    return out
+
+
+def rle_counts_to_runs(counts):
+    return np.asarray(counts_to_runs(counts), dtype=np.uint32)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liblift_oracle.so")

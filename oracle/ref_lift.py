@@ -34,8 +34,12 @@ try:  # cv2 is what the reference erodes with (nuscenes:526-527); present in thi
 except Exception:  # pragma: no cover
     cv2 = None
 
-from cm3d_b200.frames import FOURTH_COL3, FOURTH_NONE, FOURTH_ONES, FrameSpec
-from cm3d_b200.rle import rle_counts_to_runs
+from oracle.coco_rle import counts_to_runs as rle_counts_to_runs
+
+# what row 3 of aggr_pc_points holds (the FrameSpec data model's `fourth` field): nothing (KITTI keeps
+# (N,3) rows), column 3 of the raw scan (nuScenes intensity), or ones (waymo:477-479)
+FOURTH_NONE, FOURTH_COL3, FOURTH_ONES = 0, 1, 2
+FrameSpec = object      # duck-typed: sweeps, sweep_ops, cams[].ops/.K, cam_nums, masks, fourth, close_thresh, min_dist
 
 
 # --------------------------------------------------------------------------- restated L1 helpers

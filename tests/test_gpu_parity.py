@@ -417,24 +417,34 @@ def test_fast_sqrt_exhaustive(lifter):
     assert int(bad.item()) == 0
 
 
-def test_kitti_obb_yaw_against_numpy_oracle(lifter):
-    """KITTI principal-axes box + yaw (parity UNPINNED vs open3d; graded against the written-down
-    convention in oracle/obb_oracle.py).  Tolerances: yaw 1e-3 rad (mod 2 pi), centre/extent 1e-3 m."""
+def test_kitti_hull_obb_yaw_against_open3d_oracle(lifter):
+    """KITTI box + yaw: cm3d_hull_obb (hull vertices by gift wrapping on the GPU, then open3d 0.15's
+    CreateFromPoints) against oracle/obb_oracle.py (the same published algorithm with Qhull through scipy)
+    on >= 200 instances of full-size C3 frames.  The hull VERTEX SETS must have equal sizes; yaw within
+    1e-3 rad (mod 2 pi), centre / extents within 1e-3 m wherever the principal axes are well conditioned.
+    Unpinned against the open3d binary only in the sign convention of the eigenvectors."""
     from cm3d_b200 import synthetic as S
     from oracle import obb_oracle as O
-    frames = [S.make_frame("c3", i, scale=0.3) for i in range(2)]
+    frames = [S.make_frame("c3", 100 + i) for i in range(16)]
     res = lifter.lift_frames(frames, with_points=True)
-    checked = 0
+    info = lifter.last_hull_info.cpu().numpy()
+    checked = seen = k = 0
+    gap = []
     for f, r in zip(frames, res):
         assert r.obb is not None
         for i in range(f.n_instances):
             idx = r.instance_points(i)
+            k += 1
             if idx.size <= 3:                                   # kitti:1479-1480
-                assert np.isnan(r.yaw[i])
+                assert np.isnan(r.yaw[i]) and info[k - 1] == 0
                 continue
             pts = r.aggr_points[:3][:, idx].T
+            hv = O.hull_vertex_indices(pts)
+            assert info[k - 1] == len(hv), (k - 1, info[k - 1], len(hv))
+            seen += 1
             center, wlh, R = O.get_depth_bbox(pts)
-            ev = np.linalg.eigvalsh(np.cov(pts.T.astype(np.float64)))
+            v = pts[hv].astype(np.float64)
+            ev = np.linalg.eigvalsh(np.cov(v.T, bias=True))
             if min(ev[1] - ev[0], ev[2] - ev[1]) < 1e-3 * ev[2]:
                 continue                                        # near-degenerate axes: direction ill-conditioned
             yaw = O.yaw_of(R)
@@ -443,7 +453,65 @@ def test_kitti_obb_yaw_against_numpy_oracle(lifter):
             assert np.allclose(r.obb[i, 1:4], center, atol=1e-3)
             assert np.allclose(r.obb[i, 4:7], wlh, atol=1e-3)
             checked += 1
-    assert checked >= 10
+            yaw_all = O.yaw_of(O.get_depth_bbox(pts, O.allpoint_axes)[2])
+            gap.append(abs(((yaw_all - yaw + np.pi) % (2 * np.pi)) - np.pi))
+    assert seen >= 200 and checked >= 200, (seen, checked)
+    # round 1's all-point PCA really was a different estimator (the reason for this kernel)
+    assert np.median(gap) > 1e-3
+    # and the diagnostic mode reproduces it
+    lifter.obb_mode = 1
+    try:
+        res1 = lifter.lift_frames(frames[:2], with_points=True)
+    finally:
+        lifter.obb_mode = 0
+    for f, r in zip(frames[:2], res1):
+        for i in range(f.n_instances):
+            idx = r.instance_points(i)
+            if idx.size > 3:
+                pts = r.aggr_points[:3][:, idx].T
+                ev = np.linalg.eigvalsh(np.cov(pts.T.astype(np.float64)))
+                if min(ev[1] - ev[0], ev[2] - ev[1]) >= 1e-3 * ev[2]:
+                    ya = O.yaw_of(O.get_depth_bbox(pts, O.allpoint_axes)[2])
+                    assert abs(((float(r.yaw[i]) - ya + np.pi) % (2 * np.pi)) - np.pi) < 1e-3
+
+
+def test_hull_obb_flat_and_tiny_clouds_take_the_reference_fallback(lifter):
+    """Qhull rejects flat input, the reference's bare `except` then substitutes the identity box
+    (kitti:1481-1484): first point, extent 1, yaw 0.  Also exact duplicates and a cube lattice (coplanar
+    faces, collinear edges): the vertex set is the eight corners."""
+    import ctypes
+    import torch
+    from cm3d_b200 import _native as N
+    from test_pass2_functions import _segments_on_device
+    rng = np.random.default_rng(3)
+    flat = np.concatenate([rng.uniform(-3, 3, (200, 2)), np.full((200, 1), 1.5)], 1).astype(np.float32)
+    line = (np.linspace(0, 5, 50)[:, None] * np.array([[1.0, 2.0, -0.5]])).astype(np.float32)
+    same = np.repeat(np.array([[4.0, 2.0, 9.0]], np.float32), 40, 0)
+    blob = rng.normal(0, 1, (300, 3)).astype(np.float32) + np.float32(20)
+    dup = np.concatenate([blob, blob[:150]])                        # every hull vertex may exist twice
+    g = np.stack(np.meshgrid(np.arange(5.0), np.arange(4.0), np.arange(3.0)), -1).reshape(-1, 3).astype(np.float32)
+    tetra = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    sets = [flat, line, same, blob, dup, g, tetra]
+    xyzw, seg_off, seg_cap, _ = _segments_on_device(sets)
+    I = len(sets)
+    obb = torch.empty(16 * I, dtype=torch.float32, device="cuda")
+    info = torch.empty(I, dtype=torch.int32, device="cuda")
+    err = torch.zeros(4, dtype=torch.int32, device="cuda")
+    words = int(N.load().cm3d_hull_obb_ws_words(seg_cap))
+    ws = torch.empty(words, dtype=torch.int32, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    N.call("cm3d_hull_obb", p(xyzw), seg_cap, p(seg_off), I, 4, 0, p(ws), words, p(obb), p(info), p(err),
+           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    obb, info = obb.cpu().numpy().reshape(I, 16), info.cpu().numpy()
+    for k in range(3):                                              # flat / collinear / single point
+        assert info[k] == -1 and obb[k, 0] == 0.0
+        assert np.array_equal(obb[k, 1:4], sets[k][0]) and np.array_equal(obb[k, 4:7], [1, 1, 1])
+        assert np.array_equal(obb[k, 7:16].reshape(3, 3), np.eye(3))
+    from scipy.spatial import ConvexHull
+    assert info[3] == len(ConvexHull(blob.astype(np.float64)).vertices)
+    assert info[4] == info[3]                                       # duplicates add no vertex
+    assert abs(info[5]) in (8, 9)                                   # the lattice's eight corners (face count may be flagged)
+    assert info[6] == 4
 
 
 def test_nearest_lane_bit_exact_vs_scipy(lifter):

@@ -250,6 +250,12 @@ def test_cull_planes_random_cameras_and_boundary_points():
         tref = np.asarray(ops[0][1], np.float32) if ops[0][0] == "T" else np.zeros(3, np.float32)
         planes, flags = cull_planes(cam, W, H, np.float32(2.3), tref)
         assert flags == 1
+        if kind == 0:
+            # the camera that defines tref has NO residual first translation: its margin must not scale with the
+            # kilometres of |tw| (tau counts |t_c - tref|, not |t_c + tref|); depth plane: d = (c2_z - min_dist) / 1.75
+            c2 = c - M @ tref.astype(np.float64)
+            margin = float(planes[0, 3]) - (c2[2] - float(np.float32(2.3))) / 1.75
+            assert 0 < margin < 1e-3, (trial, margin)
         q = (p + tref[:, None]).astype(np.float32).astype(np.float64)
         Sq = np.abs(q).sum(0)
         val = planes[:, :3].astype(np.float64) @ q + planes[:, 3:4].astype(np.float64)
