@@ -118,6 +118,7 @@ __device__ bool hull_beats(const HullPts &P, const HullEdge &E, int a, int b)
     double lx, ly, lz, hx, hy, hz;
     P.get(lo, lx, ly, lz);
     P.get(hi, hx, hy, hz);
+    if (lx == hx && ly == hy && lz == hz) return b == lo;     // duplicate points: always the lower index (one copy per vertex)
     lx -= E.sx; ly -= E.sy; lz -= E.sz;
     hx -= E.sx; hy -= E.sy; hz -= E.sz;
     const double nlx = E.ey * lz - E.ez * ly, nly = E.ez * lx - E.ex * lz, nlz = E.ex * ly - E.ey * lx;   // e x w_lo
