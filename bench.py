@@ -30,23 +30,36 @@ sys.path.insert(0, ROOT)
 
 METRIC = "pseudo_label_frames_per_s"
 UNIT = "frames/s"
-WORKLOAD = "C2: nuScenes-shaped 10 sweeps x 34,720 pts (~347k pts) x 6 cams 1024x576 masks x 50 instances per frame"
+MASK_INPUT = "COCO counts strings (pycocotools format), decoded on the GPU"
+# BASELINE.json configs.  `gen` is the synthetic generator's config name (c5 = independent C2-shaped frames),
+# `batch` the frames per GPU and launch sequence, `stream` the DISTINCT frames per GPU of the streaming legs.
+CONFIGS = {
+    "c2": dict(gen="c5", batch=64, stream=1024, cycles=8,
+               workload="C2: nuScenes-shaped 10 sweeps x 34,720 pts (~347k pts) x 6 cams 1024x576 masks x 50 instances per frame"),
+    "c1": dict(gen="c1", batch=64, stream=512, cycles=16,
+               workload="C1: nuScenes-shaped single sample, 1 sweep (~34.7k pts) x 6 cams 1024x576 masks x 20 instances per frame"),
+    "c3": dict(gen="c3", batch=32, stream=256, cycles=8,
+               workload="C3: KITTI-shaped 64-beam (~120k pts) x 1 cam, 1024x309 masks x 15 instances per frame"),
+    "c4": dict(gen="c4", batch=16, stream=128, cycles=8,
+               workload="C4: Waymo-shaped top LiDAR (~180k pts) x 5 cams, 1024x683 / 1024x473 masks x 80 instances per frame"),
+}
 
 
-def _gen_frame(index):
+def _gen_frame(arg):
+    gen, index = arg
     from cm3d_b200 import synthetic as S
-    f = S.make_frame("c5", index, dense_masks=False)         # C5 = independent C2-shaped frames
+    f = S.make_frame(gen, index, dense_masks=False)
     f.masks = S.compress_rles(f.masks)                       # masks as in {f}_masks.pkl: COCO counts strings
     return f
 
 
-def make_frames(first, count, workers):
-    idx = list(range(first, first + count))
+def make_frames(gen, first, count, workers):
+    idx = [(gen, i) for i in range(first, first + count)]
     if workers <= 1 or count <= 2:
         return [_gen_frame(i) for i in idx]
     import multiprocessing as mp
     with mp.get_context("spawn").Pool(workers) as pool:
-        return pool.map(_gen_frame, idx)
+        return pool.map(_gen_frame, idx, chunksize=max(1, count // (8 * workers)))
 
 
 class ClockSampler:
@@ -143,22 +156,21 @@ def measured_peak():
 
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_run(frames, threads):
-    """The reference's per-frame body (oracle/ref_lift.py, torch CPU) over `frames`; seconds."""
+    """The reference's per-frame body (oracle/ref_lift.py, torch CPU) over `frames`; (seconds, results)."""
     import torch
     from oracle import ref_lift as RL
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
-    for f in frames:
-        RL.lift_frame(f, record_pix=False)
-    return time.perf_counter() - t0
+    out = [RL.lift_frame(f, record_pix=False) for f in frames]
+    return time.perf_counter() - t0, out
 
 
-def _ref_worker(index):
+def _ref_worker(arg):
     """One frame through the CPU port on ONE thread (frame-parallel CPU baseline); returns seconds."""
     import torch
     torch.set_num_threads(1)
     from oracle import ref_lift as RL
-    f = _gen_frame(index)
+    f = _gen_frame(arg)
     RL.lift_frame(_gen_frame_small(), record_pix=False)          # page in torch, untimed
     t0 = time.perf_counter()
     RL.lift_frame(f, record_pix=False)
@@ -170,11 +182,11 @@ def _gen_frame_small():
     return S.make_frame("c1", 0, scale=0.1)
 
 
-def cpu_frame_parallel(n_procs):
+def cpu_frame_parallel(gen, n_procs):
     """Frames/s of the CPU port run one process per core, one frame each, all at the same time."""
     import multiprocessing as mp
     with mp.get_context("spawn").Pool(n_procs) as pool:
-        secs = pool.map(_ref_worker, list(range(1000, 1000 + n_procs)), chunksize=1)
+        secs = pool.map(_ref_worker, [(gen, i) for i in range(100000, 100000 + n_procs)], chunksize=1)
     return sum(1.0 / s for s in secs), secs
 
 
@@ -182,20 +194,21 @@ def run_reference(args, rank):
     if rank != 0:
         return
     import torch
+    cfg = CONFIGS[args.config]
     threads = os.cpu_count() or 1
     nf = max(1, args.ref_frames)
-    frames = make_frames(0, nf, 1)
+    frames = make_frames(cfg["gen"], 0, nf, 1)
     for _ in range(args.warmup):
         cpu_reference_run(frames[:1], threads)
-    times = [cpu_reference_run(frames, threads) for _ in range(args.steps)]
+    times = [cpu_reference_run(frames, threads)[0] for _ in range(args.steps)]
     total = sum(times)
     v = nf * args.steps / total
-    sample = f"{nf} C2 frame(s) per step x {args.steps} steps, oracle/ref_lift.py (torch {torch.__version__} CPU)"
+    sample = f"{nf} {args.config.upper()} frame(s) per step x {args.steps} steps, oracle/ref_lift.py (torch {torch.__version__} CPU)"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": nf, "mask_input": "COCO counts strings (pycocotools format), decoded on the GPU"},
+        "config": {"workload": cfg["workload"], "frames_per_step": nf, "mask_input": MASK_INPUT},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -204,11 +217,75 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def _frame_labels(lab, pb, k):
+    """(member counts, medoid point index, centroids) of frame k of a packed batch from its label block."""
+    import numpy as np
+    i0, i1 = int(pb.frame_inst[k]), int(pb.frame_inst[k + 1])
+    so = lab["seg_off"].astype(np.int64)
+    return np.diff(so[i0:i1 + 1]), lab["medoid_point_idx"][i0:i1].copy(), lab["centroid"][i0:i1, :3].copy()
+
+
+def _labels_equal_oracle(gpu, o):
+    """GPU labels of one frame against the CPU oracle's (oracle/ref_lift.py): member counts, medoid point
+    index, centroid bit patterns (the medoid is a copy of an input point, so tolerance 0)."""
+    import numpy as np
+    cnt, mpi, cen = gpu
+    want_cnt = np.array([len(x) for x in o["idx"]], np.int64)
+    has = o["medoid_local"] >= 0
+    return bool(np.array_equal(cnt, want_cnt) and np.array_equal(mpi.astype(np.int64), o["medoid_point_idx"].astype(np.int64)) and
+                np.array_equal(cen[has].view(np.uint32), o["centroids"][has].astype(np.float32).view(np.uint32)) and
+                bool(np.isnan(cen[~has]).all()))
+
+
+def _disk_leg(frames, lifter, n_sweeps):
+    """The drop-in nuScenes script (src/nuscenes/2d_to_3d.py -> nuscenes_stage.run) over an on-disk synthetic
+    dataset: .bin sweeps, {f}_masks.pkl, {f}_data.json in, pseudolabels JSON out; seconds per frame include
+    every file read, the packer, H2D, kernels, pass 2, NMS and the JSON write."""
+    import importlib.util
+    import shutil
+    import tempfile
+    from cm3d_b200 import synthetic_datasets as SD
+    per_scene = 32
+    n_scenes = max(1, min(4, len(frames) // per_scene))
+    scenes = {f"scene-{k:04d}": frames[k * per_scene:(k + 1) * per_scene] for k in range(n_scenes)}
+    work = tempfile.mkdtemp(prefix="cm3d_disk_")
+    try:
+        t_w = time.perf_counter()
+        nusc, map_factory = SD.write_nuscenes(os.path.join(work, "nusc"), os.path.join(work, "masks"), scenes, ratio=0.64)
+        t_w = time.perf_counter() - t_w
+        spec = importlib.util.spec_from_file_location("nusc_script_bench", os.path.join(ROOT, "src", "nuscenes", "2d_to_3d.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.INPUT_PATH, mod.INPUT_DIR, mod.OUTPUT_DIR = os.path.join(work, "nusc"), os.path.join(work, "masks"), os.path.join(work, "out")
+        mod.n_sweeps, mod.BATCH_FRAMES = n_sweeps, 32
+        import contextlib
+        import io
+        names = list(scenes)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod.main(nusc, map_factory, names[:1], lifter=lifter)               # warm-up: one scene
+            t0 = time.perf_counter()
+            final = mod.main(nusc, map_factory, names, lifter=lifter)
+            dt = time.perf_counter() - t0
+        n_frames = n_scenes * per_scene
+        n_boxes = sum(len(v) for v in final["results"].values())
+        nbytes = sum(os.path.getsize(os.path.join(dp, fn)) for dp, _, fns in os.walk(work) for fn in fns)
+        return {"value": n_frames / dt, "unit": UNIT, "frames": n_frames, "scenes": n_scenes, "boxes_after_nms": n_boxes,
+                "dataset_bytes": nbytes, "dataset_write_seconds": round(t_w, 2),
+                "note": "src/nuscenes/2d_to_3d.py end to end on an on-disk synthetic nuScenes tree (page-cache warm): devkit record "
+                        "lookups, np.fromfile of the sweeps, pickle/json of the masks on reader threads, C packer, H2D, kernels, "
+                        "lane lookup, pass 2, circle NMS and the JSON write inside the timed region"}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def run_ours(args, rank, world, local_rank):
+    cfg = CONFIGS[args.config]
+    B = args.batch or cfg["batch"]
+    n_stream = max(B, (args.stream_frames or cfg["stream"]) // B * B)
     # frames first (spawned workers), CUDA afterwards
-    workers = max(1, min(args.workers or (os.cpu_count() or 1) // max(world, 1), 16))
+    workers = max(1, min(args.workers or (os.cpu_count() or 1) // max(world, 1), 32))
     t_gen = time.perf_counter()
-    frames = make_frames(rank * args.batch, args.batch, workers)
+    frames = make_frames(cfg["gen"], rank * n_stream, n_stream, workers)
     t_gen = time.perf_counter() - t_gen
 
     import numpy as np
@@ -221,152 +298,225 @@ def run_ours(args, rank, world, local_rank):
     from cm3d_b200.lifter import Lifter
 
     lifter = Lifter(dev)
-    pb = lifter.pack(frames)
-    db = lifter.upload(pb)
-    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- find the segment capacity once (exact), then warm up
-    do = lifter.run(db)
-    labels = lifter.fetch_labels(do)
-    need = lifter.check_flags(labels)
-    seg_total = int(labels["seg_off"][-1])
-    seg_cap = max(need, seg_total) + 4096
-    n_points = int(labels["frame_n"].sum())
-    items = int(labels["item_off"][-1])
-    so = labels["seg_off"].astype(np.int64)
-    m = np.diff(so)
-    pairs = float((m.astype(np.float64) ** 2).sum())
-    del do
-    for _ in range(max(args.warmup, 3)):
-        lifter.run(db, seg_cap=seg_cap)
+    # ---- resident batches: up to 8 DISTINCT batches of B frames live in HBM; a step lifts one of them
+    n_res = max(1, min(8, n_stream // B))
+    pbs = [lifter.pack(frames[k * B:(k + 1) * B], keep_fourth=False) for k in range(n_res)]
+    dbs = [lifter.upload(pb) for pb in pbs]
+    torch.cuda.synchronize()
+    first_labels, caps, n_points, seg_totals, pairs = [], [], [], [], []
+    for db in dbs:                      # segment capacity of every resident batch (exact, found once, untimed)
+        do = lifter.run(db)
+        lab = lifter.fetch_labels(do)
+        need = lifter.check_flags(lab)
+        if need:
+            do = lifter.run(db, seg_cap=need)
+            lab = lifter.fetch_labels(do)
+            assert lifter.check_flags(lab) == 0
+        first_labels.append(lab)
+        caps.append(int(lab["seg_off"][-1]))
+        n_points.append(int(lab["frame_n"].sum()))
+        m = np.diff(lab["seg_off"].astype(np.int64))
+        seg_totals.append(int(m.sum()))
+        pairs.append(float((m.astype(np.float64) ** 2).sum()))
+        del do
+    seg_cap = max(caps) + 4096
+    for w in range(max(args.warmup, 3)):
+        lifter.run(dbs[w % n_res], seg_cap=seg_cap)
     barrier()
 
-    # ---- device-resident timed region (CUDA events on the launch stream, per-kernel events inside)
+    # ---- device-resident timed region: CUDA events on the launch stream, nothing else inside
     sampler = ClockSampler(local_rank)
     sampler.start()
-    lifter.timing = {}
+    lifter.timing = None
     lifter.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     do = None
-    for _ in range(args.steps):
+    for k in range(args.steps):
         del do                          # free the previous step's buffers first: no second workspace, no cudaMalloc
-        do = lifter.run(db, seg_cap=seg_cap)
+        do = lifter.run(dbs[k % n_res], seg_cap=seg_cap)
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = lifter.launches
-    timing = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in lifter.timing.items()}
-    lifter.timing = None
     final = lifter.fetch_labels(do)
     assert lifter.check_flags(final) == 0
+    last = (args.steps - 1) % n_res
+    assert np.array_equal(final["medoid_point_idx"], first_labels[last]["medoid_point_idx"])       # deterministic labels
+    del do
+
+    # ---- per-kernel CUDA events: a separate pass over every resident batch (not inside the headline region)
+    lifter.timing = {}
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for db in dbs:
+        do = lifter.run(db, seg_cap=seg_cap)
+        del do
+    p1.record()
+    torch.cuda.synchronize()
+    pass_ms = p0.elapsed_time(p1) / n_res
+    timing = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in lifter.timing.items()}
+    lifter.timing = None
+    do = lifter.run(dbs[0], seg_cap=seg_cap)
     screen_modes = lifter.last_screen_modes.cpu().numpy() if lifter.last_screen_modes is not None else None
     screen_verified = int(lifter.last_screen_stats.item()) if lifter.last_screen_stats is not None else None
+    del do
 
     # ---- host->device copy rate of one packed batch (explains e2e when PCIe, not the kernels, bounds it)
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lifter.upload(pb)
+    lifter.upload(pbs[0])
     torch.cuda.synchronize()
     h0.record()
     for _ in range(3):
-        lifter.upload(pb)
+        lifter.upload(pbs[0])
     h1.record()
     torch.cuda.synchronize()
-    h2d_gbps = 3 * pb.h2d_bytes / (h0.elapsed_time(h1) * 1e-3) / 1e9
+    h2d_gbps = 3 * pbs[0].h2d_bytes / (h0.elapsed_time(h1) * 1e-3) / 1e9
 
-    # ---- end to end: pinned host buffers -> H2D -> kernels -> D2H of the labels, every step.  A step's
-    # frames go through the public streaming API in sub-batches (same frames, same order): the copy of
-    # sub-batch k+1 overlaps the kernels of sub-batch k, and only the very first copy is exposed
-    sub = max(1, min(args.e2e_sub or args.batch, args.batch))
-    subs = [lifter.pack(frames[i:i + sub]) for i in range(0, len(frames), sub)] if sub < args.batch else [pb]
-    sub_cap = seg_cap
-    if len(subs) > 1:                   # segment capacity of the largest sub-batch (exact, found once, untimed)
-        sub_cap = 4096 + max(int(lifter.fetch_labels(lifter.run(lifter.upload(p)))["seg_off"][-1]) for p in subs)
-    for lab in lifter.lift_packed_stream(subs * 3, seg_cap=sub_cap):
+    # ---- end to end: pinned host buffers -> H2D -> kernels -> D2H of the labels, every step, through the public
+    # streaming API.  A step's B frames travel as sub-batches (same frames, same order): the copy of sub-batch
+    # k+1 overlaps the kernels of sub-batch k; segment capacity is the lifter's own estimate (a batch that does
+    # not fit is rerun inside the timed region)
+    sub = max(1, min(args.e2e_sub or B, B))
+    if sub < B:
+        subs = [[lifter.pack(frames[k * B + i:k * B + i + sub], keep_fourth=False) for i in range(0, B, sub)] for k in range(n_res)]
+    else:
+        subs = [[pb] for pb in pbs]
+    seq = lambda steps: [p for k in range(steps) for p in subs[k % n_res]]
+    lifter.cap_retries = 0
+    for lab in lifter.lift_packed_stream(seq(max(3, min(n_res, 8)))):
         pass
     barrier()
+    retries0 = lifter.cap_retries
     t0 = time.perf_counter()
     labs = []
-    for lab in lifter.lift_packed_stream(subs * args.steps, seg_cap=sub_cap):
+    for lab in lifter.lift_packed_stream(seq(args.steps)):
         labs.append(lab["medoid_point_idx"])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    assert np.array_equal(np.concatenate(labs[-len(subs):]), final["medoid_point_idx"])
-    d2h_bytes = sum(int(lifter._out_layout(p.n_frames, p.n_inst)["_words"]) * 4 for p in subs)
-    h2d_bytes = sum(p.h2d_bytes for p in subs)
+    per = len(subs[0])
+    assert np.array_equal(np.concatenate(labs[-per:]), first_labels[last]["medoid_point_idx"])
+    d2h_bytes = sum(int(lifter._out_layout(p.n_frames, p.n_inst)["_words"]) * 4 for p in subs[0])
+    h2d_bytes = sum(p.h2d_bytes for p in subs[0])
+    e2e_retries = lifter.cap_retries - retries0
 
-    # ---- the same frames as FrameSpecs (what the drop-in scripts hand over): host packing included
-    fs_fps = None
-    if world == 1 and not args.no_framespec_leg:
-        fs_kw = dict(batch_frames=16, pack_workers=4)       # small batches: the packers start the pipeline sooner
-        for _ in lifter.lift_frame_stream(iter(frames * 2), **fs_kw):     # also fills the pinned-buffer pool
+    # ---- C5-style stream: every one of this rank's DISTINCT FrameSpecs (what the drop-in scripts hand over: numpy
+    # sweeps + counts strings + calibration), cycled until the timed region is seconds long - host packing, pinned
+    # pool reuse, capacity estimates and retries included
+    fs = None
+    if not args.no_framespec_leg:
+        pw = max(2, min(args.pack_workers or 8, (os.cpu_count() or 2) // max(world, 1)))
+        fs_kw = dict(batch_frames=32, pack_workers=pw)
+        for _ in lifter.lift_frame_stream(iter(frames[:min(len(frames), 8 * 32)]), **fs_kw):     # also fills the pinned-buffer pool
             pass
+        barrier()
+        cycles = max(1, args.stream_cycles or cfg["cycles"])
+        r0 = lifter.cap_retries
         t0 = time.perf_counter()
-        n_fs = 0
-        for res in lifter.lift_frame_stream(iter(frames * 4), **fs_kw):
-            n_fs += len(res)
+        n_fs = n_boxes = 0
+        for c in range(cycles):
+            for res in lifter.lift_frame_stream(iter(frames), **fs_kw):
+                n_fs += len(res)
+                n_boxes += sum(int((r.medoid_local >= 0).sum()) for r in res)
         torch.cuda.synchronize()
-        fs_fps = n_fs / (time.perf_counter() - t0)
+        fs = {"seconds": time.perf_counter() - t0, "frames": n_fs, "centroids": n_boxes, "retries": lifter.cap_retries - r0,
+              "pack_workers": pw, "cycles": cycles}
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- parity witnesses
+    parity = {}
+    if world > 1:       # one sampled frame of another rank, recomputed alone on rank 0
+        src = world - 1
+        mine = np.full(256, -2, np.int32)
+        mp_ = _frame_labels(first_labels[0], pbs[0], 0)[1]
+        mine[:min(256, mp_.size)] = mp_[:256]
+        t_all = [torch.empty(256, dtype=torch.int32, device=dev) for _ in range(world)]
+        dist.all_gather(t_all, torch.from_numpy(mine).to(dev))
+        if rank == 0:
+            f_src = _gen_frame((cfg["gen"], src * n_stream))
+            r = lifter.lift_frames([f_src], with_points=False)[0]
+            want = np.full(256, -2, np.int32)
+            want[:min(256, r.medoid_point_idx.size)] = r.medoid_point_idx[:256]
+            ok = bool(np.array_equal(t_all[src].cpu().numpy(), want))
+            parity["cross_rank"] = {"rank": src, "frame": src * n_stream, "equal": ok,
+                                    "what": "medoid point indices of that rank's first frame == a single-frame recomputation on rank 0"}
+            assert ok, "cross-rank parity witness failed"
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, fs["seconds"] * 1e3 if fs else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, fs_ms = float(t[0]), float(t[1]), float(t[2])
+    cnt = torch.tensor([fs["frames"] if fs else 0, fs["retries"] if fs else 0, e2e_retries], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    fs_frames_all, fs_retries_all, e2e_retries_all = (int(v) for v in cnt)
 
     if rank == 0:
-        total_frames = args.batch * world * args.steps
+        total_frames = B * world * args.steps
         value = total_frames / (dev_ms * 1e-3)
         e2e = total_frames / (e2e_ms * 1e-3)
         peak, peak_src = measured_peak()
-        raw_bytes = int(pb.raw.nbytes)
-        algo = {   # algorithmic bytes per launch (DESIGN.md "Kernels and rooflines")
-            "aggregate": raw_bytes + 16 * n_points,
-            "project_count": 16 * n_points,
-            "compact": 4 * n_points + 36 * seg_total,
-            "masks_decode": int(pb.mask.nbytes) * 5,
-            "masks_rle": int(pb.mask.nbytes) * 4 + 4 * pb.bits_words,
-            "masks_erode": 8 * pb.bits_words,
+        mean = lambda v: float(np.mean(v))
+        raw_bytes = mean([int(pb.raw.nbytes) for pb in pbs])
+        npts, segt = mean(n_points), mean(seg_totals)
+        bits_words = mean([pb.bits_words for pb in pbs])
+        mask_bytes = mean([int(pb.mask.nbytes) for pb in pbs])
+        algo = {   # algorithmic bytes per launch (DESIGN.md "Kernels and rooflines"), mean over the resident batches
+            "aggregate": raw_bytes + 12 * npts,
+            "project_count": 16 * npts,
+            "compact": 4 * npts + 28 * segt,          # hit words in; per member: xyz in, index + xyz out
+            "masks_decode": mask_bytes * 5,
+            "masks_rle": mask_bytes * 4 + 4 * bits_words,
+            "masks_erode": 8 * bits_words,
         }
+        step_ms = dev_ms / args.steps
         kern = {}
         for k, ms in timing.items():
-            kern[k] = {"ms": ms, "share": ms * args.steps / dev_ms}
+            kern[k] = {"ms": ms, "share": ms / pass_ms}
             if k in algo:
-                kern[k]["algo_bytes"] = algo[k]
+                kern[k]["algo_bytes"] = int(algo[k])
                 kern[k]["gbps"] = algo[k] / (ms * 1e-3) / 1e9
         hbm_k = max((k for k in kern if k in ("aggregate", "project_count", "compact")), key=lambda k: kern[k]["ms"])
-        traffic, traffic_src = None, None
-        try:        # DRAM bytes per launch of that kernel from the newest committed ncu capture of this same command
+        traffic, traffic_src, erode_dram = None, None, None
+        try:        # DRAM bytes per launch from the newest committed ncu capture of this same command
             cands = sorted(fn for fn in os.listdir(os.path.join(ROOT, "profiles")) if fn.endswith("_traffic.json"))
             with open(os.path.join(ROOT, "profiles", cands[-1])) as f:
                 tj = json.load(f)
-            if tj.get("frames_per_launch") == args.batch:
+            if tj.get("frames_per_launch") == B and tj.get("config", "c2") == args.config:
                 traffic, traffic_src = tj["dram_bytes_per_launch"].get("k_" + hbm_k), tj["source"]
+                erode_dram = tj["dram_bytes_per_launch"].get("k_erode3x3")
         except Exception:
             pass
+        if erode_dram and "masks_erode" in kern:     # rows without set pixels are written unread: report the DRAM rate too
+            kern["masks_erode"]["dram_bytes_ncu"] = erode_dram
+            kern["masks_erode"]["dram_gbps"] = erode_dram / (kern["masks_erode"]["ms"] * 1e-3) / 1e9
         roof = {"kernel": hbm_k, "bound": "hbm", "achieved": kern[hbm_k]["gbps"], "peak": peak, "unit": "GB/s",
                 "frac": kern[hbm_k]["gbps"] / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "algo_bytes": algo[hbm_k], "peak_source": peak_src}
+                "algo_bytes": int(algo[hbm_k]), "peak_source": peak_src,
+                "timing": "CUDA events around the C-ABI call on its launch stream, mean over a separate pass across the resident batches"}
         if "medoid" in timing:
-            kern["medoid"]["pair_distances"] = pairs
-            kern["medoid"]["gpairs_per_s"] = pairs / (timing["medoid"] * 1e-3) / 1e9
+            prs = mean(pairs)
+            kern["medoid"]["pair_distances"] = prs
+            kern["medoid"]["gpairs_per_s"] = prs / (timing["medoid"] * 1e-3) / 1e9
             # XU-pipe ceiling: one MUFU square root per EVALUATED pair and the XU pipe retires
             # 16 lanes per SM and clock.  Instances whose squared-distance matrix is exactly symmetric
             # (mode 2) are screened over the pairs i <= j of 256-column strips: about half the roots.
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             mhz = clocks.get("sm_mhz") or 1965.0
             ceil_roots = n_sm * 16 * mhz * 1e6 / 1e9
-            roots = pairs
+            m0 = np.diff(first_labels[0]["seg_off"].astype(np.int64))
+            roots = float((m0.astype(np.float64) ** 2).sum())
             if screen_modes is not None:
-                I_ = m.size
+                I_ = m0.size
                 modes, g0, g1 = screen_modes[:I_], screen_modes[I_:2 * I_].astype(np.float64), screen_modes[2 * I_:3 * I_].astype(np.float64)
-                mm = m.astype(np.float64)
+                mm = m0.astype(np.float64)
 
                 def tri(x):      # roots of a symmetric strip sweep over x points: pairs i <= j by 256-column strips
                     fb = np.floor(x / 256.0)
@@ -377,6 +527,7 @@ def run_ours(args, rank, world, local_rank):
                 kern["medoid"]["instances_by_mode"] = {"exact": int((modes == 0).sum()), "screen_all_pairs": int((modes == 1).sum()),
                                                        "screen_symmetric": int((modes == 2).sum()),
                                                        "screen_grouped_symmetric": int((modes == 3).sum())}
+            roots *= prs / max(pairs[0], 1.0)        # batch 0's root count scaled to the mean batch
             kern["medoid"]["bound"] = ("XU pipe: one MUFU.SQRT per evaluated pair distance in the screen pass (reads only "
                                        "sum M points, L2-resident); symmetric instances evaluate the pairs i <= j only")
             kern["medoid"]["square_roots"] = roots
@@ -386,34 +537,40 @@ def run_ours(args, rank, world, local_rank):
             if screen_verified is not None:
                 kern["medoid"]["screen_min_pts"] = lifter.screen_min_pts
                 kern["medoid"]["verified_columns_per_step"] = screen_verified
-                kern["medoid"]["instances_per_step"] = int(m.size)
+                kern["medoid"]["instances_per_step"] = int(m0.size)
+        inter_mb = 4 * 5 * mean([pb.n_tiles for pb in pbs]) * 1024 / 1e6
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": args.batch, "mask_input": "COCO counts strings (pycocotools format), decoded on the GPU",
-                       "points_per_step": n_points, "member_points_per_step": seg_total,
-                       "l2": f"inputs per step {pb.h2d_bytes / 1e6:.0f} MB + {4 * 5 * pb.n_tiles * 1024 / 1e6:.0f} MB "
-                             f"intermediates > 126 MB L2, no explicit flush",
+            "config": {"workload": cfg["workload"], "frames_per_gpu_per_step": B, "mask_input": MASK_INPUT,
+                       "distinct_resident_batches_per_gpu": n_res, "distinct_frames_per_gpu": n_stream,
+                       "points_per_step": int(npts), "member_points_per_step": int(segt),
+                       "point_columns_shipped": "x, y, z (the 4th column never reaches a label: nuscenes:645,656)",
+                       "l2": f"a step reads one of {n_res} distinct resident batches: {pbs[0].h2d_bytes / 1e6:.0f} MB inputs + {inter_mb:.0f} MB "
+                             f"intermediates per step > 126 MB L2, no explicit flush",
                        "parallelism": f"frames sharded by sample index, {world} process(es), no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_gbps_rank0": round(h2d_gbps, 1), "sub_batch_frames": sub,
-                    "api": "Lifter.lift_packed_stream (pinned host buffers in, label block out)"},
+                    "h2d_gbps_rank0": round(h2d_gbps, 1), "sub_batch_frames": sub, "capacity_retries": e2e_retries_all,
+                    "api": "Lifter.lift_packed_stream (pinned host buffers in, label block out), distinct batches, the lifter's own capacity estimate"},
             "gpu_launches": launches,
-            "e2e_from_framespecs": None if fs_fps is None else {
-                "value": fs_fps, "unit": UNIT,
-                "note": "Lifter.lift_frame_stream over 4 x the step's FrameSpecs (numpy sweeps + RLE masks + calibration): "
-                        "C packer (csrc/pack.cu, ~0.9 ms per frame and thread, GIL released) on 4 worker threads into "
-                        "pooled pinned buffers, 16-frame batches"},
+            "e2e_from_framespecs": None if fs is None else {
+                "value": fs_frames_all / (fs_ms * 1e-3), "unit": UNIT, "frames": fs_frames_all, "seconds": fs_ms * 1e-3,
+                "distinct_frames_per_gpu": n_stream, "cycles": fs["cycles"], "capacity_retries": fs_retries_all,
+                "pack_workers_per_gpu": fs["pack_workers"], "vs_value": fs_frames_all / (fs_ms * 1e-3) / value,
+                "note": "Lifter.lift_frame_stream over every distinct FrameSpec of the rank (numpy sweeps + counts strings + calibration), "
+                        "cycled: C packer (csrc/pack.cu, GIL released) on worker threads into pooled pinned buffers, 32-frame batches, "
+                        "H2D / kernels / D2H pipelined; wall clock, max over ranks"},
             "roofline": roof,
             "path_hbm": {"algorithmic_bytes_per_step": int(sum(algo.values())) * world,
-                         "achieved_gbps": sum(algo.values()) * world / (dev_ms / args.steps * 1e-3) / 1e9,
-                         "frac_of_peak_per_gpu": sum(algo.values()) / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
+                         "achieved_gbps": sum(algo.values()) * world / (step_ms * 1e-3) / 1e9,
+                         "frac_of_peak_per_gpu": sum(algo.values()) / (step_ms * 1e-3) / 1e9 / peak,
                          "note": "sum of the kernels' algorithmic bytes over the whole step; the step is bound by the "
                                  "medoid's square roots (XU pipe), not by HBM (kernels.medoid)"},
             "kernels": kern,
+            "kernel_pass_ms_per_step": pass_ms,
             "gen_seconds": round(t_gen, 1),
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -421,22 +578,67 @@ def run_ours(args, rank, world, local_rank):
             nf = max(1, args.ref_frames)
             from cm3d_b200 import synthetic as S
             cpu_reference_run([S.make_frame("c1", 0, scale=0.25)], threads)      # spin up the torch thread pool
-            secs = cpu_reference_run(frames[:nf], threads)
+            secs, outs = cpu_reference_run(frames[:nf], threads)
             line["cpu_baseline"] = {"value": nf / secs, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{nf} of this step's C2 frames through oracle/ref_lift.py "
+                                    "sample": f"{nf} of this run's {args.config.upper()} frames through oracle/ref_lift.py "
                                               f"(torch {torch.__version__} CPU, {threads} threads), after a small warm-up frame"}
+            eq = [_labels_equal_oracle(_frame_labels(first_labels[0], pbs[0], k), outs[k]) for k in range(nf)]
+            parity["oracle"] = {"frames": nf, "instances": int(sum(len(o["idx"]) for o in outs)), "equal": bool(all(eq)),
+                                "what": "GPU labels of the cpu_baseline frames == oracle/ref_lift.py: member counts, medoid point index, centroid bits"}
+            assert all(eq), "bench frames: GPU labels differ from the CPU oracle"
             if not args.no_frame_parallel:
-                try:      # one single-threaded process per core, one C2 frame each, concurrently
-                    fp, per = cpu_frame_parallel(threads)
+                try:      # one single-threaded process per core, one frame each, concurrently
+                    fp, per = cpu_frame_parallel(cfg["gen"], threads)
                     line["cpu_baseline"]["frame_parallel"] = {
                         "value": fp, "unit": UNIT, "processes": threads,
-                        "sample": f"{threads} C2 frames, one per process, 1 torch thread each, run concurrently; "
+                        "sample": f"{threads} {args.config.upper()} frames, one per process, 1 torch thread each, run concurrently; "
                                   f"sum of 1/seconds (mean {sum(per) / len(per):.1f} s per frame)"}
                 except Exception as e:
                     line["cpu_baseline"]["frame_parallel"] = {"error": repr(e)[:200]}
+        line["parity_checked"] = parity
+        if world == 1 and args.config == "c2" and not args.no_disk_leg:
+            try:
+                line["e2e_from_disk"] = _disk_leg(frames, lifter, n_sweeps=10)
+            except Exception as e:
+                line["e2e_from_disk"] = {"error": repr(e)[:300]}
+        if world == 1 and not args.no_latency_leg:
+            try:
+                line["latency_batch1"] = _latency_leg(frames, lifter)
+            except Exception as e:
+                line["latency_batch1"] = {"error": repr(e)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _latency_leg(frames, lifter):
+    """One frame per call (BASELINE config 1's "single sample"): host FrameSpec in, labels out, synchronous."""
+    import numpy as np
+    import torch
+    fr = frames[:16]
+    for f in fr[:4]:
+        lifter.lift_frames([f], with_points=False, keep_fourth=False)
+    torch.cuda.synchronize()
+    ts = []
+    for f in fr:
+        t0 = time.perf_counter()
+        lifter.lift_frames([f], with_points=False, keep_fourth=False)
+        ts.append(time.perf_counter() - t0)
+    out = {"ms_median": 1e3 * float(np.median(ts)), "ms_min": 1e3 * float(np.min(ts)), "frames": len(ts),
+           "api": "Lifter.lift_frames([frame]) - pack, H2D, launch sequence, D2H, synchronous"}
+    if hasattr(lifter, "lift_frame_graph"):
+        g = lifter.lift_frame_graph(fr[0])                 # capture once for this frame geometry
+        for f in fr[:4]:
+            g.lift(f)
+        tg = []
+        for f in fr:
+            t0 = time.perf_counter()
+            g.lift(f)
+            tg.append(time.perf_counter() - t0)
+        out["graph_ms_median"] = 1e3 * float(np.median(tg))
+        out["graph_ms_min"] = 1e3 * float(np.min(tg))
+        out["graph_api"] = "Lifter.lift_frame_graph(frame).lift(frame): preallocated workspace, the launch sequence replayed as one CUDA graph"
+    return out
 
 
 def main():
@@ -444,16 +646,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
-    ap.add_argument("--e2e-sub", type=int, default=0,
-                    help="frames per pipelined sub-batch of the end-to-end leg (0 = the whole batch; 16 measured 1.3 %% "
-                         "slower on one GPU: the host's per-batch enqueue work stops hiding behind 5.6 ms of kernels)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config (default: the one the metric is quoted on)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (0 = the config's default: 64 for C2)")
+    ap.add_argument("--stream-frames", type=int, default=0, help="distinct frames per GPU of the streaming legs (0 = config default: 1024 for C2)")
+    ap.add_argument("--stream-cycles", type=int, default=0, help="passes over the distinct frames in the FrameSpec leg (0 = config default)")
+    ap.add_argument("--e2e-sub", type=int, default=32, help="frames per pipelined sub-batch of the end-to-end leg (0 = the whole batch)")
+    ap.add_argument("--pack-workers", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-frames", type=int, default=2, help="frames of the CPU sample")
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame-parallel", action="store_true", help="skip the one-process-per-core CPU baseline")
     ap.add_argument("--no-framespec-leg", action="store_true", help="skip the FrameSpec-level (host packing included) leg")
+    ap.add_argument("--no-disk-leg", action="store_true", help="skip the on-disk drop-in script leg")
+    ap.add_argument("--no-latency-leg", action="store_true", help="skip the one-frame-per-call latency leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -18,7 +18,7 @@ from typing import Dict, List, Sequence
 
 import numpy as np
 
-from .frames import CHAIN_WORDS, FOURTH_NONE, FrameSpec, RLEMask, encode_chain
+from .frames import CHAIN_WORDS, FOURTH_COL3, FOURTH_NONE, FrameSpec, RLEMask, encode_chain
 from .rle import rle_counts_to_runs
 
 TILE = 1024
@@ -262,7 +262,14 @@ class PackedBatch:
         return int(self.raw.nbytes + self.meta.nbytes + self.mask.nbytes + self.mask_off.nbytes)
 
 
-def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
+def _eff_fourth(f: FrameSpec, keep_fourth: bool) -> int:
+    """What row 3 of the aggregated cloud holds ON THE DEVICE: the frame's own `fourth`, or nothing when the
+    caller does not read point rows back.  No output of the reference depends on it (the medoid takes
+    `[:3]`, the centroid `points[:3]`: nuscenes:645,656), and it is a quarter of the sweep bytes."""
+    return f.fourth if keep_fourth else FOURTH_NONE
+
+
+def pack_frames(frames: Sequence[FrameSpec], pin: bool = False, keep_fourth: bool = True) -> PackedBatch:
     F = len(frames)
     if F == 0:
         raise ValueError("empty batch")
@@ -279,11 +286,12 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
     n_inst = sum(f.n_instances for f in frames)
     sweep_tiles, raw_off = [], []
     ro = 0
-    def packed(s):      # nuScenes rows are (x, y, z, intensity, ring index): the fifth column is never read
-        return s[:, :4] if s.shape[1] == 5 else s
+    def packed(s, fourth):      # only the columns the kernels read travel: x, y, z (+ column 3 when it becomes row 3)
+        ncol = 4 if fourth == FOURTH_COL3 else 3
+        return s[:, :ncol] if s.shape[1] != ncol else s
     for f in frames:
         for s in f.sweeps:
-            s = packed(s)
+            s = packed(s, _eff_fourth(f, keep_fourth))
             if s.shape[0] == 0:
                 sweep_tiles.append(0)
                 raw_off.append(ro)
@@ -317,14 +325,14 @@ def pack_frames(frames: Sequence[FrameSpec], pin: bool = False) -> PackedBatch:
         max_inst_pf = max(max_inst_pf, I)
         t_begin = ti
         for s_local, (s, ops) in enumerate(zip(f.sweeps, f.sweep_ops)):
-            s = packed(s)
+            s = packed(s, _eff_fourth(f, keep_fourth))
             nt = sweep_tiles[si]
             o = raw_off[si]
             raw[o:o + s.size] = s.reshape(-1)
             pad = ((s.size + 3) & ~3) - s.size
             if pad:
                 raw[o + s.size:o + s.size + pad] = 0
-            sweep_desc[si] = [*_split64(o), s.shape[0], s.shape[1], fi, ti, len(chains), f.fourth]
+            sweep_desc[si] = [*_split64(o), s.shape[0], s.shape[1], fi, ti, len(chains), _eff_fourth(f, keep_fourth)]
             chains.append(encode_chain(ops))
             tile_sweep[ti:ti + nt] = si
             ti += nt
@@ -472,7 +480,8 @@ def _ptr_of(a: np.ndarray) -> int:
     return a.__array_interface__["data"][0]
 
 
-def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "PinnedPool" = None) -> PackedBatch:
+def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "PinnedPool" = None,
+                       keep_fourth: bool = True) -> PackedBatch:
     """pack_frames through the C packer of the library (csrc/pack.cu): the FrameSpecs are flattened into
     pointer / size arrays here, everything else - the copy of the raw sweeps into (pinned) memory, the
     descriptor tables, the fp64 cull planes - happens in one ctypes call that holds no GIL, so several
@@ -485,11 +494,11 @@ def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "Pi
         raise ValueError("empty batch")
     for f in frames:
         if isinstance(f.masks, np.ndarray) or any(not isinstance(m.counts, (bytes, str)) for m in f.masks):
-            return pack_frames(frames, pin)
+            return pack_frames(frames, pin, keep_fourth)
     if not any(f.n_instances for f in frames):
-        return pack_frames(frames, pin)
+        return pack_frames(frames, pin, keep_fourth)
     if any(len(o) > 4 for f in frames for o in f.sweep_ops) or any(len(c.ops) > 4 for f in frames for c in f.cams):
-        return pack_frames(frames, pin)              # raises the chain-length error with its message
+        return pack_frames(frames, pin, keep_fourth)              # raises the chain-length error with its message
     lib = N.load()
 
     sw_ptr, sw_npts, sw_stride, op_begin, op_kind, op_ptr, cam_K = [], [], [], [0], [], [], []
@@ -523,7 +532,7 @@ def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "Pi
     f32 = lambda v: np.asarray(v, np.float32)
     arrs = dict(
         fr_n_sweeps=i32([len(f.sweeps) for f in frames]), fr_n_cams=i32([len(f.cams) for f in frames]),
-        fr_n_inst=i32([f.n_instances for f in frames]), fr_fourth=i32([f.fourth for f in frames]),
+        fr_n_inst=i32([f.n_instances for f in frames]), fr_fourth=i32([_eff_fourth(f, keep_fourth) for f in frames]),
         fr_min_pts=i32([4 if f.dataset == "kitti" else 1 for f in frames]),
         fr_use_close=i32([f.close_thresh is not None for f in frames]),
         fr_use_floor=i32([f.floor_thresh is not None for f in frames]),
@@ -543,7 +552,7 @@ def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "Pi
     plan = np.zeros(16, np.int64)
     rc = lib.cm3d_pack_plan(ctypes.byref(inp), ctypes.c_void_p(_ptr_of(plan)))
     if rc != 0:
-        return pack_frames(frames, pin)          # raises the per-frame limit error with its message
+        return pack_frames(frames, pin, keep_fourth)          # raises the per-frame limit error with its message
     n_tiles, n_vcams, n_chains = int(plan[0]), int(plan[1]), int(plan[2])
     taken = []
     raw, raw_t = _alloc(int(plan[3]), np.float32, pin, pool, taken)

@@ -41,7 +41,8 @@ int op_size(int kind) { return kind == CM3D_OP_T ? 3 : (kind == CM3D_OP_R ? 9 : 
 
 // nuScenes .bin rows are (x, y, z, intensity, ring index): nothing downstream reads the fifth column
 // (src/nuscenes/utils/pcd.py:246-257 keeps four), so it does not travel to the GPU.
-int64_t packed_stride(int64_t stride) { return stride == 5 ? 4 : stride; }
+// only the columns the kernels read travel: x, y, z (+ column 3 when it becomes row 3 of the cloud, fourth == 1)
+int64_t packed_stride(int fourth) { return fourth == 1 ? 4 : 3; }
 
 void encode_chain(const OpRef *ops, int n, uint32_t *out)
 {
@@ -168,7 +169,7 @@ int cm3d_pack_plan(const cm3d_pack_input *in, int64_t *plan)
             n_pts += n;
             if (n == 0) continue;
             n_tiles += (n + CM3D_TILE - 1) / CM3D_TILE;
-            raw += align4(n * packed_stride(in->sw_stride[si]));
+            raw += align4(n * packed_stride(in->fr_fourth[f]));
         }
         const int I = in->fr_n_inst[f];
         if (I > CM3D_MAX_INST) return CM3D_ELIMIT;
@@ -217,7 +218,7 @@ int cm3d_pack_fill(const cm3d_pack_input *in, const int64_t *plan, float *raw, i
         const int I = in->fr_n_inst[f];
         const int t_begin = ti;
         for (int s = 0; s < in->fr_n_sweeps[f]; ++s, ++si) {
-            const int64_t n = in->sw_npts[si], stride_in = in->sw_stride[si], stride = packed_stride(stride_in);
+            const int64_t n = in->sw_npts[si], stride_in = in->sw_stride[si], stride = packed_stride(in->fr_fourth[f]);
             const int64_t o = ro;
             int nt = 0;
             if (n > 0) {
@@ -225,9 +226,12 @@ int cm3d_pack_fill(const cm3d_pack_input *in, const int64_t *plan, float *raw, i
                 const float *src = reinterpret_cast<const float *>(in->sw_ptr[si]);
                 if (stride == stride_in) {
                     memcpy(raw + o, src, (size_t)(n * stride) * 4);
-                } else {
+                } else if (stride == 4) {
                     float *dst = raw + o;
                     for (int64_t k = 0; k < n; ++k) memcpy(dst + 4 * k, src + stride_in * k, 16);
+                } else {
+                    float *dst = raw + o;
+                    for (int64_t k = 0; k < n; ++k) memcpy(dst + 3 * k, src + stride_in * k, 12);
                 }
                 for (int64_t k = n * stride; k < align4(n * stride); ++k) raw[o + k] = 0.0f;
                 ro += align4(n * stride);

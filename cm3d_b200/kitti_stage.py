@@ -128,17 +128,20 @@ def run(cfg, kitti=None, frame_range=None, lifter=None) -> int:
     todo = [f for f in (frame_range if frame_range is not None else range(len(kitti))) if f % world == rank]
     pending = []
 
+    def build(frame_num):
+        t0 = time.time()
+        masks, data = load_frame_masks(cfg.INPUT_DIR, None, frame_num)
+        for p in (os.path.join(cfg.PRED_DIR, f"{frame_num:06}.txt"), os.path.join(cfg.PSEUDO_DIR, f"{frame_num:06}.txt")):
+            if os.path.exists(p):
+                os.remove(p)
+            open(p, "a").close()
+        return frame_spec(kitti, frame_num, masks, data, cfg), frame_num, data, time.time() - t0
+
     def frames():
-        for frame_num in todo:
-            t0 = time.time()
-            masks, data = load_frame_masks(cfg.INPUT_DIR, None, frame_num)
-            for p in (os.path.join(cfg.PRED_DIR, f"{frame_num:06}.txt"), os.path.join(cfg.PSEUDO_DIR, f"{frame_num:06}.txt")):
-                if os.path.exists(p):
-                    os.remove(p)
-                open(p, "a").close()
-            spec = frame_spec(kitti, frame_num, masks, data, cfg)
+        from .lifter import prefetch_map                     # files are read on reader threads, in frame order
+        for spec, frame_num, data, dt in prefetch_map(build, todo, getattr(cfg, "reader_threads", 8)):
             pending.append((frame_num, data))
-            timer["io"] += time.time() - t0
+            timer["io"] += dt
             yield spec
 
     written = 0

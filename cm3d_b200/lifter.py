@@ -106,6 +106,29 @@ def merge_split(results: List[LiftResult], parts: Sequence[int]) -> List[LiftRes
     return out
 
 
+def prefetch_map(fn, items, workers: int = 8, depth: int = 0):
+    """Ordered `map(fn, items)` on reader threads with a bounded look-ahead: the drop-in scripts build their
+    FrameSpecs with it (np.fromfile of the sweeps, pickle / json of the masks and the devkit record
+    lookups run while earlier frames are being packed, copied and lifted).  The reference reads its
+    files serially inside the frame loop (src/nuscenes/2d_to_3d.py:422-438)."""
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    workers = max(1, int(workers))
+    depth = depth or 2 * workers
+    if workers == 1:
+        for x in items:
+            yield fn(x)
+        return
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        pending = deque()
+        for x in items:
+            pending.append(pool.submit(fn, x))
+            if len(pending) >= depth:
+                yield pending.popleft().result()
+        while pending:
+            yield pending.popleft().result()
+
+
 def _on_device(fn):
     """Run a Lifter method with the lifter's GPU as the current CUDA device (generators included)."""
     import functools
@@ -152,6 +175,7 @@ class Lifter:
         self.denoise = None         # default-off extensions, see run()
         self.box_search = None
         self.launches = 0           # kernels launched by this object (bench.py reports it)
+        self.cap_retries = 0        # streamed batches rerun because the segment buffers were too small
         self.screen_min_pts = SCREEN_MIN_PTS   # medoid: instances this large are screened, then verified; 0 = all exact
         self.screen_flags = 0                  # bit 0: no symmetric screen (every screened instance does all M^2 pairs);
         #                                        bit 1: no grouped symmetric screen for instances that straddle two binades
@@ -174,15 +198,19 @@ class Lifter:
         self.timing.setdefault(label, []).append((a, b))
 
     # ------------------------------------------------------------------ host -> device
-    def pack(self, frames: Sequence[FrameSpec]) -> PackedBatch:
+    def pack(self, frames: Sequence[FrameSpec], keep_fourth: bool = True) -> PackedBatch:
+        """FrameSpecs -> pinned host buffers.  keep_fourth=False leaves the 4th point column (nuScenes
+        intensity, KITTI reflectance) on the host: nothing the reference outputs reads it, and it is a
+        quarter of the bytes that cross PCIe; only LiftResult.aggr_points row 3 needs it."""
         # the C packer (csrc/pack.cu) for batches whose masks are counts strings, the Python packer otherwise
-        return pack_frames_native(frames, pin=True)
+        return pack_frames_native(frames, pin=True, keep_fourth=keep_fourth)
 
     def _pack_pooled(self, frames: Sequence[FrameSpec]) -> PackedBatch:
-        """pack() into pinned buffers of this Lifter's pool; the streaming path releases them after use."""
+        """pack() into pinned buffers of this Lifter's pool; the streaming path releases them after use.
+        The streaming path returns labels only, so the 4th point column stays on the host."""
         if self._pin_pool is None:
             self._pin_pool = PinnedPool()
-        return pack_frames_native(frames, pin=True, pool=self._pin_pool)
+        return pack_frames_native(frames, pin=True, pool=self._pin_pool, keep_fourth=False)
 
     @_on_device
     def upload(self, pb: PackedBatch) -> DeviceBatch:
@@ -470,6 +498,7 @@ class Lifter:
                 ratio = max(need, int(lab["seg_off"][-1])) / pb.n_raw_points
                 self._seg_ratio = ratio if self._seg_ratio is None else max(0.95 * self._seg_ratio, ratio)
             if need:                        # rare: rerun this batch synchronously with exact capacity
+                self.cap_retries += 1
                 with torch.cuda.stream(comp_s):
                     do = self.run(db, seg_cap=need)
                     lab = self.fetch_labels(do)
@@ -549,11 +578,13 @@ class Lifter:
 
     @_on_device
     def lift_frames(self, frames: Sequence[FrameSpec], with_points: bool = True, with_pix: bool = False,
-                    want_col_sums: bool = False, denoise=None, box_search: Optional[int] = None) -> List[LiftResult]:
+                    want_col_sums: bool = False, denoise=None, box_search: Optional[int] = None,
+                    keep_fourth: Optional[bool] = None) -> List[LiftResult]:
         """Synchronous convenience: pack, upload, run, read back; retries once with exact
-        segment capacity if the default guess was too small."""
+        segment capacity if the default guess was too small.  The 4th point column travels only when
+        point rows are read back (keep_fourth defaults to with_points)."""
         frames, parts = split_oversize(frames, MAX_INST)
-        pb = self.pack(frames)
+        pb = self.pack(frames, keep_fourth=with_points if keep_fourth is None else keep_fourth)
         db = self.upload(pb)
         kw = dict(want_pix=with_pix, want_col_sums=want_col_sums, denoise=denoise, box_search=box_search)
         do = self.run(db, **kw)

@@ -39,7 +39,7 @@ DEFAULTS = dict(
     ATTRIBUTE_NAMES=B.ATTRIBUTE_NAMES, DEVICE="cuda:0",
     min_dist=2.3, floor_thresh=0.6, ratio=0.64, n_sweeps=3, pointsensor_channel="LIDAR_TOP",
     shape_priors_path="cfg/shape_priors_chatgpt.json", output_name="pseudolabels_minival.json",
-    threshs_by_label=B.THRESHS_BY_LABEL, batch_frames=32,
+    threshs_by_label=B.THRESHS_BY_LABEL, batch_frames=32, reader_threads=8,
 )
 
 
@@ -151,20 +151,26 @@ def lift_scene(nusc, scene_name: str, cfg, lifter, timer) -> dict:
     num_frames = count_frames(nusc, sample)
     out = {"samples": [], "data": [], "lidar_pose": [], "centroid_ids": [], "centroids": []}
 
+    samples = [sample]                                  # the scene's sample chain (nuscenes:413-415, :693-694)
+    while len(samples) < num_frames:
+        samples.append(nusc.get("sample", samples[-1]["next"]))
+
+    def build(frame_num):
+        t0 = time.time()
+        s = samples[frame_num]
+        masks, data = load_frame_masks(cfg.INPUT_DIR, scene_name, frame_num)
+        spec = frame_spec(nusc, s, masks, data, cfg)
+        ps = nusc.get("sample_data", s["data"][cfg.pointsensor_channel])
+        return spec, s["token"], data, nusc.get("ego_pose", ps["ego_pose_token"]), time.time() - t0
+
     def frames():
-        s = sample
-        for frame_num in range(num_frames):
-            t0 = time.time()
-            masks, data = load_frame_masks(cfg.INPUT_DIR, scene_name, frame_num)
-            spec = frame_spec(nusc, s, masks, data, cfg)
-            ps = nusc.get("sample_data", s["data"][cfg.pointsensor_channel])
-            out["samples"].append(s["token"])
+        from .lifter import prefetch_map
+        for spec, token, data, pose, dt in prefetch_map(build, range(num_frames), getattr(cfg, "reader_threads", 8)):
+            out["samples"].append(token)
             out["data"].append(data)
-            out["lidar_pose"].append(nusc.get("ego_pose", ps["ego_pose_token"]))
-            timer["io"] += time.time() - t0
+            out["lidar_pose"].append(pose)
+            timer["io"] += dt
             yield spec
-            if s["next"] != "":
-                s = nusc.get("sample", s["next"])
 
     id_offset = 0
     for res_batch in lifter.lift_frame_stream(frames(), batch_frames=cfg.batch_frames, timer=timer):

@@ -55,7 +55,7 @@ OUTPUT_NAME = "pseudolabels_minival.json"
 BATCH_FRAMES = 32             # frames per GPU launch sequence (not in the reference)
 
 
-def main(nusc=None, nusc_map_factory=None, scene_names=None):
+def main(nusc=None, nusc_map_factory=None, scene_names=None, lifter=None):
     from cm3d_b200 import nuscenes_stage as stage
     if DEVICE == "cpu":
         raise RuntimeError("cm3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -71,7 +71,7 @@ def main(nusc=None, nusc_map_factory=None, scene_names=None):
         nusc = NuScenes(VER_NAME, INPUT_PATH, True)
         scene_names = getattr(splits, SPLIT)
         nusc_map_factory = stage.default_map_factory(INPUT_PATH)
-    return stage.run(cfg, nusc, nusc_map_factory, scene_names)
+    return stage.run(cfg, nusc, nusc_map_factory, scene_names, lifter=lifter)
 
 
 if __name__ == "__main__":

@@ -76,9 +76,12 @@ def test_pack_frames_tables():
         o = int(np.uint32(sd[s, 0])) | (int(sd[s, 1]) << 32)
         assert o % 4 == 0                                   # 16-byte aligned sweep starts (bulk copy)
         t += nt
-    # raw points are copied verbatim
+    # raw points: the columns the kernels read, verbatim (KITTI: x, y, z - its reflectance column is never read)
     o = int(np.uint32(sd[3, 0]))
-    assert np.array_equal(pb.raw[o:o + frames[1].sweeps[0].size], frames[1].sweeps[0].reshape(-1))
+    kxyz = frames[1].sweeps[0][:, :3]
+    assert sd[3, 3] == 3 and np.array_equal(pb.raw[o:o + kxyz.size], kxyz.reshape(-1))
+    o = int(np.uint32(sd[0, 0]))
+    assert sd[0, 3] == 4 and np.array_equal(pb.raw[o:o + 4 * frames[0].sweeps[0].shape[0]], frames[0].sweeps[0][:, :4].reshape(-1))
     # instances: frame-major, vcam lists partition the frame's instances
     assert pb.n_inst == sum(f.n_instances for f in frames)
     vd = pb.table("vcam_desc", B.VC_WORDS)
@@ -307,9 +310,13 @@ def test_native_packer_equals_python_packer():
         elif not all(isinstance(m.counts, (bytes, str)) for m in f.masks):
             f.masks = compress_rles(f.masks)
     empty = dataclasses.replace(frames[0], sweeps=[np.zeros((0, 5), np.float32)] + frames[0].sweeps[1:])
-    for batch in (frames, frames[:1], [frames[2]], [empty, frames[1]]):
-        a, b = B.pack_frames(batch), B.pack_frames_native(batch)
+    for batch, keep in ((frames, True), (frames[:1], True), ([frames[2]], True), ([empty, frames[1]], True),
+                        (frames, False), ([empty, frames[1]], False)):
+        a, b = B.pack_frames(batch, keep_fourth=keep), B.pack_frames_native(batch, keep_fourth=keep)
         assert b.masks_kind == "rle_str" == a.masks_kind
+        # only the columns the kernels read are packed: 4 floats per point when column 3 becomes row 3, else 3
+        want = sum((-(-s.size // s.shape[1] * (4 if (keep and f.fourth == 1) else 3) // 4)) * 4 for f in batch for s in f.sweeps if s.shape[0])
+        assert a.raw.size == want + 4
         for name in ("n_frames", "n_sweeps", "n_tiles", "n_vcams", "n_inst", "n_chains", "max_inst_per_frame", "cnt_total",
                      "bits_words", "max_words", "n_raw_points", "max_runs", "grid_words", "max_cells", "any_kitti",
                      "frame_datasets", "frame_vcam_cams"):
