@@ -389,7 +389,11 @@ def run_ours(args, rank, world, local_rank):
         subs = [[lifter.pack(frames[k * B + i:k * B + i + sub], keep_fourth=False) for i in range(0, B, sub)] for k in range(n_res)]
     else:
         subs = [[pb] for pb in pbs]
-    seq = lambda steps: [p for k in range(steps) for p in subs[k % n_res]]
+    # pipeline ramp-up: the very first copy of a stream is the only one nothing overlaps, so the first step's batch
+    # travels in small pieces (same frames, same order); every later step is one whole batch
+    ramp = max(0, min(args.e2e_ramp, B))
+    first = [lifter.pack(frames[i:i + ramp], keep_fourth=False) for i in range(0, B, ramp)] if 0 < ramp < B else subs[0]
+    seq = lambda steps: [p for k in range(steps) for p in (first if k == 0 else subs[k % n_res])]
     lifter.cap_retries = 0
     for lab in lifter.lift_packed_stream(seq(max(3, min(n_res, 8)))):
         pass
@@ -413,22 +417,25 @@ def run_ours(args, rank, world, local_rank):
     # pool reuse, capacity estimates and retries included
     fs = None
     if not args.no_framespec_leg:
-        pw = max(2, min(args.pack_workers or 8, (os.cpu_count() or 2) // max(world, 1)))
-        fs_kw = dict(batch_frames=32, pack_workers=pw)
+        # measured on the 16-vCPU box: 6 packer threads feed the GPU (3.8 k frames/s); 8 or 12 slow the launching thread down
+        pw = max(2, min(args.pack_workers or 6, (os.cpu_count() or 2) // max(world, 1) - 1))
+        fs_kw = dict(batch_frames=args.stream_batch, pack_workers=pw)
         for _ in lifter.lift_frame_stream(iter(frames[:min(len(frames), 8 * 32)]), **fs_kw):     # also fills the pinned-buffer pool
             pass
         barrier()
         cycles = max(1, args.stream_cycles or cfg["cycles"])
+        lifter.stream_stats.clear()
         r0 = lifter.cap_retries
         t0 = time.perf_counter()
         n_fs = n_boxes = 0
-        for c in range(cycles):
-            for res in lifter.lift_frame_stream(iter(frames), **fs_kw):
-                n_fs += len(res)
-                n_boxes += sum(int((r.medoid_local >= 0).sum()) for r in res)
+        import itertools
+        for res in lifter.lift_frame_stream(itertools.chain.from_iterable(frames for _ in range(cycles)), **fs_kw):     # ONE stream
+            n_fs += len(res)
+            n_boxes += sum(int((r.medoid_local >= 0).sum()) for r in res)
         torch.cuda.synchronize()
         fs = {"seconds": time.perf_counter() - t0, "frames": n_fs, "centroids": n_boxes, "retries": lifter.cap_retries - r0,
-              "pack_workers": pw, "cycles": cycles}
+              "pack_workers": pw, "cycles": cycles, "stats": {k: round(v, 3) for k, v in lifter.stream_stats.items()},
+              "pinned_allocations": lifter._pin_pool.allocations if lifter._pin_pool is not None else None}
 
     # ---- parity witnesses
     parity = {}
@@ -553,15 +560,17 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_gbps_rank0": round(h2d_gbps, 1), "sub_batch_frames": sub, "capacity_retries": e2e_retries_all,
+                    "h2d_gbps_rank0": round(h2d_gbps, 1), "sub_batch_frames": sub, "first_step_piece_frames": ramp or B,
+                    "capacity_retries": e2e_retries_all,
                     "api": "Lifter.lift_packed_stream (pinned host buffers in, label block out), distinct batches, the lifter's own capacity estimate"},
             "gpu_launches": launches,
             "e2e_from_framespecs": None if fs is None else {
                 "value": fs_frames_all / (fs_ms * 1e-3), "unit": UNIT, "frames": fs_frames_all, "seconds": fs_ms * 1e-3,
                 "distinct_frames_per_gpu": n_stream, "cycles": fs["cycles"], "capacity_retries": fs_retries_all,
                 "pack_workers_per_gpu": fs["pack_workers"], "vs_value": fs_frames_all / (fs_ms * 1e-3) / value,
+                "rank0_seconds_waiting": fs["stats"], "rank0_pinned_allocations": fs["pinned_allocations"],
                 "note": "Lifter.lift_frame_stream over every distinct FrameSpec of the rank (numpy sweeps + counts strings + calibration), "
-                        "cycled: C packer (csrc/pack.cu, GIL released) on worker threads into pooled pinned buffers, 32-frame batches, "
+                        "cycled: C packer (csrc/pack.cu, GIL released) on worker threads into pooled pinned buffers, "
                         "H2D / kernels / D2H pipelined; wall clock, max over ranks"},
             "roofline": roof,
             "path_hbm": {"algorithmic_bytes_per_step": int(sum(algo.values())) * world,
@@ -650,8 +659,11 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (0 = the config's default: 64 for C2)")
     ap.add_argument("--stream-frames", type=int, default=0, help="distinct frames per GPU of the streaming legs (0 = config default: 1024 for C2)")
     ap.add_argument("--stream-cycles", type=int, default=0, help="passes over the distinct frames in the FrameSpec leg (0 = config default)")
-    ap.add_argument("--e2e-sub", type=int, default=32, help="frames per pipelined sub-batch of the end-to-end leg (0 = the whole batch)")
+    ap.add_argument("--e2e-sub", type=int, default=0, help="frames per pipelined sub-batch of the end-to-end leg (0 = the whole batch; "
+                    "32 measured 2.8 %% slower on one GPU: two launch sequences per step have two medoid tails)")
+    ap.add_argument("--e2e-ramp", type=int, default=16, help="frames per piece of the FIRST step of the end-to-end leg (0 = no ramp-up)")
     ap.add_argument("--pack-workers", type=int, default=0)
+    ap.add_argument("--stream-batch", type=int, default=32, help="frames per launch sequence of the FrameSpec stream leg")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-frames", type=int, default=2, help="frames of the CPU sample")
     ap.add_argument("--workers", type=int, default=0)

@@ -175,10 +175,13 @@ class PinnedPool:
     take() hands out a pinned uint8 tensor of at least `nbytes`; give() returns it once the batch's
     host->device copies are done (PackedBatch.release)."""
 
-    def __init__(self):
+    def __init__(self, max_bytes: int = 24 << 30):
         import threading
         self._lock = threading.Lock()
         self._free = []
+        self._free_bytes = 0
+        self.max_bytes = int(max_bytes)
+        self.allocations = 0                  # cudaHostAlloc calls so far (a warm stream makes none)
 
     def take(self, nbytes: int):
         import torch
@@ -186,17 +189,22 @@ class PinnedPool:
         with self._lock:
             best = -1
             for k, t in enumerate(self._free):           # smallest buffer that fits, but not a giant for a small request
-                if nbytes <= t.numel() <= max(4 * nbytes, 1 << 16) and (best < 0 or t.numel() < self._free[best].numel()):
+                if nbytes <= t.numel() <= max(2 * nbytes, 1 << 16) and (best < 0 or t.numel() < self._free[best].numel()):
                     best = k
             if best >= 0:
-                return self._free.pop(best)
-        return torch.empty((nbytes * 5 // 4 + 4095) & ~4095, dtype=torch.uint8, pin_memory=True)     # head room: batches vary
+                t = self._free.pop(best)
+                self._free_bytes -= t.numel()
+                return t
+            self.allocations += 1
+        size = max(nbytes * 5 // 4, 1 << 16)             # head room: batches vary; small tables share one size class
+        return torch.empty((size + 4095) & ~4095, dtype=torch.uint8, pin_memory=True)
 
     def give(self, tensors):
         with self._lock:
-            self._free.extend(tensors)
-            if len(self._free) > 64:                      # keep the largest ones
-                self._free = sorted(self._free, key=lambda x: -x.numel())[:64]
+            for t in tensors:
+                if self._free_bytes + t.numel() <= self.max_bytes:
+                    self._free.append(t)
+                    self._free_bytes += t.numel()
 
 
 def _alloc(n, dtype, pin, pool=None, taken=None):
@@ -501,20 +509,30 @@ def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "Pi
         return pack_frames(frames, pin, keep_fourth)              # raises the chain-length error with its message
     lib = N.load()
 
-    sw_ptr, sw_npts, sw_stride, op_begin, op_kind, op_ptr, cam_K = [], [], [], [0], [], [], []
-    keep = []                                    # arrays whose memory the C side reads
+    # Every small matrix of the batch (chain ops, intrinsics) is gathered into ONE float32 blob with a single
+    # concatenate; the C side gets pointers into it (base + offset).  A per-matrix pointer lookup costs 2 us of
+    # GIL time, 2.6k of them per 32-frame batch would be a third of the stream's per-frame budget.
+    sw_ptr, sw_npts, sw_stride, op_begin, op_kind, mats, k_slot = [], [], [], [0], [], [], []
     for f in frames:
         for s, ops in zip(f.sweeps, f.sweep_ops):
             sw_ptr.append(_ptr_of(s)); sw_npts.append(s.shape[0]); sw_stride.append(s.shape[1])
             for kind, m in ops:
-                op_kind.append(_KIND_CODE[kind]); op_ptr.append(_ptr_of(m))
+                op_kind.append(_KIND_CODE[kind]); mats.append(m.reshape(-1))
             op_begin.append(len(op_kind))
     for f in frames:
         for cam in f.cams:
             for kind, m in cam.ops:
-                op_kind.append(_KIND_CODE[kind]); op_ptr.append(_ptr_of(m))
+                op_kind.append(_KIND_CODE[kind]); mats.append(m.reshape(-1))
             op_begin.append(len(op_kind))
-            cam_K.append(_ptr_of(cam.K))
+            k_slot.append(len(mats)); mats.append(cam.K.reshape(-1))
+    sizes_ = np.fromiter(map(len, mats), np.int64, len(mats))
+    starts = np.zeros(len(mats) + 1, np.int64)
+    np.cumsum(sizes_, out=starts[1:])
+    mat_blob = np.concatenate(mats).astype(np.float32, copy=False) if mats else np.zeros(1, np.float32)
+    mat_ptr = (np.uint64(_ptr_of(mat_blob)) + (starts[:-1] * 4).astype(np.uint64))
+    is_k = np.zeros(len(mats), bool)
+    is_k[k_slot] = True
+    op_ptr, cam_K = mat_ptr[~is_k], mat_ptr[is_k]
     counts = []
     for f in frames:
         for m in f.masks:
@@ -540,12 +558,12 @@ def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "Pi
         fr_min_dist=f32([f.min_dist_f32() for f in frames]),
         fr_floor=f32([0.0 if f.floor_thresh is None else f.floor_thresh for f in frames]),
         sw_ptr=np.asarray(sw_ptr, np.uint64), sw_npts=i32(sw_npts), sw_stride=i32(sw_stride),
-        op_begin=i32(op_begin), op_kind=i32(op_kind), op_ptr=np.asarray(op_ptr, np.uint64),
-        cam_K=np.asarray(cam_K, np.uint64), in_cam=in_cam, in_W=in_W, in_H=in_H, in_counts_off=in_counts_off)
+        op_begin=i32(op_begin), op_kind=i32(op_kind), op_ptr=np.ascontiguousarray(op_ptr, np.uint64),
+        cam_K=np.ascontiguousarray(cam_K, np.uint64), in_cam=in_cam, in_W=in_W, in_H=in_H, in_counts_off=in_counts_off)
     global _PackInput
     if _PackInput is None:
         _PackInput = _pack_input_type()
-    inp = _PackInput(F, len(sw_ptr), len(cam_K), n_inst)
+    inp = _PackInput(F, len(sw_ptr), int(cam_K.size), n_inst)
     for k, a in arrs.items():
         setattr(inp, k, _ptr_of(a))
     inp.counts = ctypes.cast(ctypes.c_char_p(blob), ctypes.c_void_p).value

@@ -11,6 +11,10 @@
 #include <algorithm>
 #include <vector>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include "../../include/cm3d_b200.h"
 
 namespace {
@@ -43,6 +47,35 @@ int op_size(int kind) { return kind == CM3D_OP_T ? 3 : (kind == CM3D_OP_R ? 9 : 
 // (src/nuscenes/utils/pcd.py:246-257 keeps four), so it does not travel to the GPU.
 // only the columns the kernels read travel: x, y, z (+ column 3 when it becomes row 3 of the cloud, fourth == 1)
 int64_t packed_stride(int fourth) { return fourth == 1 ? 4 : 3; }
+
+// Copy the first `cols` (3 or 4) floats of n rows of `stride_in` floats into a dense (n, cols) block.
+// The destination is the pinned staging buffer the DMA engine reads next and the packer never reads back:
+// non-temporal 16-byte stores keep it out of the caches and skip the read-for-ownership of every line, a
+// quarter of the host memory traffic of a packed frame - and host memory bandwidth is what bounds the
+// FrameSpec stream once eight packer threads and the H2D copies run at the same time.
+// dst must be 16-byte aligned (sweeps start at multiples of four floats of a 4 KiB-aligned buffer).
+void pack_rows(float *dst, const float *src, int64_t n, int stride_in, int cols)
+{
+#if defined(__SSE2__)
+    if (((uintptr_t)dst & 15) == 0) {
+        int64_t k = 0;
+        if (cols == 4) {
+            for (; k < n; ++k) _mm_stream_ps(dst + 4 * k, _mm_loadu_ps(src + (int64_t)stride_in * k));
+        } else {
+            for (; k + 4 <= n; k += 4) {
+                const float *a = src + (int64_t)stride_in * k, *b = a + stride_in, *c = b + stride_in, *d = c + stride_in;
+                _mm_stream_ps(dst + 3 * k, _mm_setr_ps(a[0], a[1], a[2], b[0]));
+                _mm_stream_ps(dst + 3 * k + 4, _mm_setr_ps(b[1], b[2], c[0], c[1]));
+                _mm_stream_ps(dst + 3 * k + 8, _mm_setr_ps(c[2], d[0], d[1], d[2]));
+            }
+            for (; k < n; ++k) memcpy(dst + 3 * k, src + (int64_t)stride_in * k, 12);
+        }
+        _mm_sfence();
+        return;
+    }
+#endif
+    for (int64_t k = 0; k < n; ++k) memcpy(dst + cols * k, src + (int64_t)stride_in * k, (size_t)cols * 4);
+}
 
 void encode_chain(const OpRef *ops, int n, uint32_t *out)
 {
@@ -224,15 +257,7 @@ int cm3d_pack_fill(const cm3d_pack_input *in, const int64_t *plan, float *raw, i
             if (n > 0) {
                 nt = (int)((n + CM3D_TILE - 1) / CM3D_TILE);
                 const float *src = reinterpret_cast<const float *>(in->sw_ptr[si]);
-                if (stride == stride_in) {
-                    memcpy(raw + o, src, (size_t)(n * stride) * 4);
-                } else if (stride == 4) {
-                    float *dst = raw + o;
-                    for (int64_t k = 0; k < n; ++k) memcpy(dst + 4 * k, src + stride_in * k, 16);
-                } else {
-                    float *dst = raw + o;
-                    for (int64_t k = 0; k < n; ++k) memcpy(dst + 3 * k, src + stride_in * k, 12);
-                }
+                pack_rows(raw + o, src, n, (int)stride_in, (int)stride);
                 for (int64_t k = n * stride; k < align4(n * stride); ++k) raw[o + k] = 0.0f;
                 ro += align4(n * stride);
             }

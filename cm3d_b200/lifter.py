@@ -176,6 +176,7 @@ class Lifter:
         self.box_search = None
         self.launches = 0           # kernels launched by this object (bench.py reports it)
         self.cap_retries = 0        # streamed batches rerun because the segment buffers were too small
+        self.stream_stats = {}      # seconds the streaming path spent waiting for packers / the GPU / enqueueing (diagnostics)
         self.screen_min_pts = SCREEN_MIN_PTS   # medoid: instances this large are screened, then verified; 0 = all exact
         self.screen_flags = 0                  # bit 0: no symmetric screen (every screened instance does all M^2 pairs);
         #                                        bit 1: no grouped symmetric screen for instances that straddle two binades
@@ -435,12 +436,17 @@ class Lifter:
         part_queue = []                         # per batch: sub-frame counts of its (possibly split) frames
 
         def groups():
+            # the first batches are small (8, 8, 16 frames): the first pack + copy is the only part of a stream
+            # that nothing overlaps, so it should be short; from then on batches of batch_frames
+            ramp = [min(batch_frames, n) for n in (8, 8, 16)] if batch_frames > 16 else []
             cur, parts = [], []
             for f in frames:
                 sub, k = split_oversize([f], MAX_INST)
                 cur.extend(sub)
                 parts.extend(k)
-                if len(parts) >= batch_frames:
+                if len(parts) >= (ramp[0] if ramp else batch_frames):
+                    if ramp:
+                        ramp.pop(0)
                     part_queue.append(parts)
                     yield cur
                     cur, parts = [], []
@@ -456,21 +462,35 @@ class Lifter:
             workers = max(1, int(pack_workers))
             with ThreadPoolExecutor(max_workers=workers) as pool:
                 pending = deque()
+                def take():
+                    t = time.perf_counter()
+                    pb = pending.popleft().result()
+                    self.stream_stats["wait_pack"] = self.stream_stats.get("wait_pack", 0.0) + time.perf_counter() - t
+                    return pb
                 for g in groups():
                     pending.append(pool.submit(self._pack_pooled, g))
-                    if len(pending) > workers:
-                        yield pending.popleft().result()
+                    if len(pending) >= workers:
+                        yield take()
                 while pending:
-                    yield pending.popleft().result()
+                    yield take()
 
-        t0 = time.time()
-        for pb, do, lab in self.lift_packed_stream(batches(), depth=depth, with_handles=True):
-            res = merge_split(self.results(do, lab, with_points=False), part_queue.pop(0))
-            pb.release()                        # its pinned buffers go back to the pool: the copies are long done
-            if timer is not None:
-                timer["points in mask"] += time.time() - t0
-            yield res
+        # The packer threads hold the GIL while they flatten a batch (a few ms of Python per batch); with the
+        # default 5 ms switch interval the launching thread would queue behind them every time one of its ~60
+        # C calls per batch hands the GIL back, and the GPU would idle.  A short interval keeps the launches flowing.
+        import sys
+        old_interval = sys.getswitchinterval()
+        sys.setswitchinterval(min(old_interval, 2e-4))
+        try:
             t0 = time.time()
+            for pb, do, lab in self.lift_packed_stream(batches(), depth=depth, with_handles=True):
+                res = merge_split(self.results(do, lab, with_points=False), part_queue.pop(0))
+                pb.release()                        # its pinned buffers go back to the pool: the copies are long done
+                if timer is not None:
+                    timer["points in mask"] += time.time() - t0
+                yield res
+                t0 = time.time()
+        finally:
+            sys.setswitchinterval(old_interval)
 
     @_on_device
     def lift_packed_stream(self, batches, seg_cap: Optional[int] = None, depth: int = 2, with_handles: bool = False):
@@ -488,9 +508,14 @@ class Lifter:
         inflight = []                       # (pb, db, do, pinned, done_event)
         pool = []                           # pinned result buffers, reused (cudaHostAlloc is slow)
 
+        import time as _t
+        st = self.stream_stats
+
         def finish(item):
             pb, db, do, pinned, done = item
+            t = _t.perf_counter()
             done.synchronize()
+            st["wait_gpu"] = st.get("wait_gpu", 0.0) + _t.perf_counter() - t
             lab = self._split_labels(pinned[:do.out.numel()].numpy().copy(), do.layout)
             pool.append(pinned)
             need = self.check_flags(lab)
@@ -507,6 +532,7 @@ class Lifter:
             return (pb, do, lab) if with_handles else lab
 
         for pb in batches:
+            t_enq = _t.perf_counter()
             with torch.cuda.stream(copy_s):
                 db = self.upload(pb)
                 up = torch.cuda.Event()
@@ -514,14 +540,16 @@ class Lifter:
             with torch.cuda.stream(comp_s):
                 comp_s.wait_event(up)
                 do = self.run(db, seg_cap=seg_cap)
-                pinned = next((b for b in pool if b.numel() >= do.out.numel()), None)
-                if pinned is None:
-                    pinned = torch.empty(do.out.numel(), dtype=torch.int32, pin_memory=True)
+                k = next((k for k, b in enumerate(pool) if b.numel() >= do.out.numel()), -1)
+                if k < 0:
+                    pinned = torch.empty(max(do.out.numel(), 1 << 14), dtype=torch.int32, pin_memory=True)
                 else:
-                    pool.remove(pinned)
+                    pinned = pool.pop(k)       # (list.remove would compare tensors element-wise)
                 pinned[:do.out.numel()].copy_(do.out, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(comp_s)
+            st["enqueue"] = st.get("enqueue", 0.0) + _t.perf_counter() - t_enq
+            st["batches"] = st.get("batches", 0) + 1
             inflight.append((pb, db, do, pinned, done))
             if len(inflight) >= depth:
                 yield finish(inflight.pop(0))
