@@ -57,6 +57,7 @@ class DeviceOutputs:
     obb: Optional[torch.Tensor] = None     # (I,16): yaw, centre, wlh, R' (KITTI frames / want_obb)
     box: Optional[torch.Tensor] = None     # (I,8): orientation search (box_search=n_angles)
     seg_off_raw: Optional[torch.Tensor] = None   # (I+1,) offsets before the neighbour-count filter
+    done: Optional[object] = None                # overlap mode: event recorded after the last kernel (on the medoid stream)
 
 
 def split_oversize(frames: Sequence[FrameSpec], limit: int):
@@ -167,6 +168,7 @@ class Lifter:
         torch.cuda.set_device(self.device)
         self.seg_factor = float(seg_factor)
         N.load()
+        self._med_stream = None     # second-phase stream of run(overlap=True)
         self._streams = None        # (copy, compute) streams of the pipelined path, created once: torch's
         #                             caching allocator pools memory per stream, so fresh streams per call
         #                             would cudaMalloc the whole workspace again (~100 ms)
@@ -238,8 +240,12 @@ class Lifter:
     @_on_device
     def run(self, db: DeviceBatch, seg_cap: Optional[int] = None, want_pix: bool = False,
             want_col_sums: bool = False, do_medoid: bool = True, want_obb: Optional[bool] = None,
-            denoise=None, box_search: Optional[int] = None) -> DeviceOutputs:
-        """One launch sequence over a packed batch.  Default-off extensions (not executed by the
+            denoise=None, box_search: Optional[int] = None, overlap: bool = False) -> DeviceOutputs:
+        """One launch sequence over a packed batch.  `overlap=True` (the streaming paths and bench.py): the
+        medoid and box kernels go to a second stream behind an event, so that the HBM-bound front end
+        (masks, aggregation, projection, gather) of the NEXT batch runs next to this batch's XU-bound medoid
+        when the caller launches the front ends on a higher-priority stream; `DeviceOutputs.done` is then the
+        event to wait for before touching any output.  Default-off extensions (not executed by the
         reference, parity unpinned): `denoise=(radius, min_neighbors)` drops member points with fewer
         than min_neighbors members of their instance within radius before the medoid / boxes;
         `box_search=n_angles` adds the orientation / extent search (LiftResult.box)."""
@@ -353,6 +359,39 @@ class Lifter:
             o("seg_off")[:I + 1].copy_(seg_off2[:I + 1])
             seg_point_idx, seg_xyzw = seg_point_idx2, seg_xyzw2
 
+        # ---- second phase (medoid, boxes): same stream, or the lifter's medoid stream behind an event
+        front = torch.cuda.current_stream(dev)
+        phase2 = None
+        if overlap:
+            if self._med_stream is None:
+                self._med_stream = torch.cuda.Stream(dev)
+            phase2 = self._med_stream
+            ev = torch.cuda.Event()
+            ev.record(front)
+            phase2.wait_event(ev)
+            for t in (out, seg_point_idx, seg_xyzw, medoid_best, item_inst):
+                t.record_stream(phase2)              # allocated on the front stream, read / written on the other one
+            st = ctypes.c_void_p(phase2.cuda_stream)
+        with torch.cuda.stream(phase2 if phase2 is not None else front):
+            do = self._run_phase2(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, medoid_best, item_inst, st,
+                                  want_col_sums, do_medoid, want_obb, box_search)
+            if phase2 is not None:
+                do.done = torch.cuda.Event()
+                do.done.record(phase2)
+        do.xyzw, do.tile_cnt, do.tile_prefix, do.pix, do.hits, do.bits, do.bbox, do.seg_off_raw = \
+            xyzw, tile_cnt, tile_prefix, pix, hits, bits, bbox, seg_off_raw
+        return do
+
+    def _run_phase2(self, db, out, lay, seg_cap, seg_point_idx, seg_xyzw, medoid_best, item_inst, st,
+                    want_col_sums, do_medoid, want_obb, box_search) -> DeviceOutputs:
+        pb, dev = db.pb, self.device
+        I = pb.n_inst
+        i32 = dict(dtype=torch.int32, device=dev)
+
+        def o(name):
+            a, n = lay[name]
+            return out[a:a + max(n, 1)]
+
         # ---- medoid (screen + verify for instances of >= screen_min_pts points, see csrc/medoid.cu)
         col_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if want_col_sums else None
         screen_stats = screen_min = None
@@ -396,8 +435,8 @@ class Lifter:
             self._call("box_search", "cm3d_box_search", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, up_axis,
                        int(box_search), 1, _ptr(box), _ptr(o("errflags")), st)
             self.launches += 1
-        return DeviceOutputs(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, xyzw, tile_cnt, tile_prefix,
-                             pix, col_sums, hits, bits, bbox, obb, box, seg_off_raw)
+        return DeviceOutputs(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, None, None, None,
+                             None, col_sums, None, None, None, obb, box, None)
 
     # ------------------------------------------------------------------ device -> host
     @_on_device
@@ -500,7 +539,8 @@ class Lifter:
         pinned memory.  A batch whose segment buffers overflow is rerun with the exact size."""
         dev = self.device
         if self._streams is None:
-            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            # front-end stream at high priority: its blocks take the SM slots the previous batch's medoid frees
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1))
         copy_s, comp_s = self._streams
         cur = torch.cuda.current_stream(dev)
         copy_s.wait_stream(cur)             # whatever the caller queued so far comes first
@@ -539,7 +579,8 @@ class Lifter:
                 up.record(copy_s)
             with torch.cuda.stream(comp_s):
                 comp_s.wait_event(up)
-                do = self.run(db, seg_cap=seg_cap)
+                do = self.run(db, seg_cap=seg_cap, overlap=True)
+            with torch.cuda.stream(self._med_stream):          # behind the medoid: labels back, then the batch is done
                 k = next((k for k, b in enumerate(pool) if b.numel() >= do.out.numel()), -1)
                 if k < 0:
                     pinned = torch.empty(max(do.out.numel(), 1 << 14), dtype=torch.int32, pin_memory=True)
@@ -547,7 +588,7 @@ class Lifter:
                     pinned = pool.pop(k)       # (list.remove would compare tensors element-wise)
                 pinned[:do.out.numel()].copy_(do.out, non_blocking=True)
                 done = torch.cuda.Event()
-                done.record(comp_s)
+                done.record(self._med_stream)
             st["enqueue"] = st.get("enqueue", 0.0) + _t.perf_counter() - t_enq
             st["batches"] = st.get("batches", 0) + 1
             inflight.append((pb, db, do, pinned, done))

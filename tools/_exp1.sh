@@ -1,4 +1,4 @@
 set -x
-for pw in 6 8 12; do
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-disk-leg --no-latency-leg --pack-workers $pw > gpurun_out/r02j_$pw.json 2> gpurun_out/r02j_$pw.err
-done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/r02k_tests.log
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-disk-leg --no-latency-leg > gpurun_out/r02k_a.json 2> gpurun_out/r02k_a.err
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-disk-leg --no-latency-leg --no-overlap --no-framespec-leg > gpurun_out/r02k_b.json 2> gpurun_out/r02k_b.err
