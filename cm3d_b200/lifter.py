@@ -169,6 +169,7 @@ class Lifter:
         self.seg_factor = float(seg_factor)
         N.load()
         self._med_stream = None     # second-phase stream of run(overlap=True)
+        self._graph_runner = None   # lift_frame_graph(): CUDA graphs by batch geometry
         self._streams = None        # (copy, compute) streams of the pipelined path, created once: torch's
         #                             caching allocator pools memory per stream, so fresh streams per call
         #                             would cudaMalloc the whole workspace again (~100 ms)
@@ -596,6 +597,15 @@ class Lifter:
                 yield finish(inflight.pop(0))
         while inflight:
             yield finish(inflight.pop(0))
+
+    def lift_frame_graph(self):
+        """Low-latency entry for one frame (or one small batch) per call: the launch sequence is captured
+        once per batch geometry as a CUDA graph over a preallocated workspace and replayed
+        (cm3d_b200/graph.py).  Returns a runner: `runner.lift(frame_or_frames) -> [LiftResult]`."""
+        from .graph import GraphRunner
+        if self._graph_runner is None:
+            self._graph_runner = GraphRunner(self)
+        return self._graph_runner
 
     def check_flags(self, labels: dict):
         e = labels["errflags"]

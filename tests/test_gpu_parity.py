@@ -792,3 +792,44 @@ def test_frame_stream_with_packer_threads_and_buffer_pool(lifter):
             assert np.array_equal(a.medoid_point_idx, b.medoid_point_idx)
             assert np.array_equal(a.centroids.view(np.uint32), b.centroids.view(np.uint32))
     assert lifter._pin_pool is not None and len(lifter._pin_pool._free) >= 4
+
+
+def test_cuda_graph_path_equals_plain_path(lifter):
+    """Lifter.lift_frame_graph(): one frame per call, launch sequence replayed as a CUDA graph - same labels as
+    lift_frames on every frame, across frames of the same and of different batch geometry."""
+    from cm3d_b200 import synthetic as S
+    frames = []
+    for cfg, idx, scale in (("c1", 0, 1.0), ("c1", 1, 1.0), ("c1", 2, 1.0), ("c2", 0, 0.25), ("c1", 3, 1.0), ("c4", 0, 0.25)):
+        f = S.make_frame(cfg, idx, scale=scale, dense_masks=False)
+        f.masks = S.compress_rles(f.masks)
+        frames.append(f)
+    g = lifter.lift_frame_graph()
+    for f in frames:
+        a = g.lift(f)[0]
+        b = lifter.lift_frames([f], with_points=False)[0]
+        assert np.array_equal(a.seg_offsets, b.seg_offsets)
+        assert np.array_equal(a.medoid_local, b.medoid_local) and np.array_equal(a.medoid_point_idx, b.medoid_point_idx)
+        assert np.array_equal(a.centroids.view(np.uint32), b.centroids.view(np.uint32))
+    assert 2 <= g.captures <= len(frames)
+
+
+def test_c5_seeds_stream_against_c_oracle(lifter):
+    """The bench's own frames (config C5: seeds 5,000,000 + i, masks as counts strings, xyz-only on the wire)
+    through the streaming entry the drop-in scripts use, against the C oracle: member counts, medoid
+    point index, centroid - bit for bit."""
+    from cm3d_b200 import synthetic as S
+    from oracle import c_oracle as CO
+    frames = []
+    for i in (0, 1, 1023):
+        f = S.make_frame("c5", i, dense_masks=False)
+        f.masks = S.compress_rles(f.masks)
+        frames.append(f)
+    res = [r for batch in lifter.lift_frame_stream(iter(frames), batch_frames=2, pack_workers=2) for r in batch]
+    assert len(res) == len(frames)
+    for f, r in zip(frames, res):
+        o = CO.lift_frame_c(f, record_pix=False)
+        assert r.n_points == o["n_points"]
+        assert np.array_equal(r.counts, [len(x) for x in o["idx"]])
+        assert np.array_equal(r.medoid_local, o["medoid_local"]) and np.array_equal(r.medoid_point_idx, o["medoid_point_idx"])
+        has = o["medoid_local"] >= 0
+        assert np.array_equal(r.centroids[has].view(np.uint32), o["centroids"][has].view(np.uint32))
