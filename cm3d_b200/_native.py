@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CM3D_B200_LIB") or os.path.join(_HERE, "_lib", "libcm3d_b200.so")   # env: kernel experiments
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -30,7 +30,7 @@ PROTOTYPES = {
     "cm3d_compact_segments": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P],
     "cm3d_medoid": [_P, _L, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "cm3d_medoid_items": [_I, _I],
-    "cm3d_hull_obb": [_P, _L, _P, _I, _I, _I, _P, _L, _P, _P, _P, _P],
+    "cm3d_hull_obb": [_P, _L, _P, _I, _I, _I, _P, _P, _L, _P, _P, _P, _P],
     "cm3d_neighbor_filter": [_P, _L, _P, _I, _I, ctypes.c_float, _I, _P, _P, _P, _P],
     "cm3d_schedule_segments": [_P, _P, _I, _L, _P, _P, _P, _P, _P, _P],
     "cm3d_filter_segments": [_P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P],

@@ -93,14 +93,14 @@ __device__ void jacobi3(double a[3][3], double v[3][3])
 }
 
 // ------------------------------------------------------------------------------------------ hull vertices
-constexpr int kHullThreads = 1024;
+constexpr int kHullThreads = 512;
 
 struct HullPts {
     const float *x, *y, *z;
     int m;
     __device__ __forceinline__ void get(int r, double &px, double &py, double &pz) const
     {
-        px = (double)__ldg(x + r); py = (double)__ldg(y + r); pz = (double)__ldg(z + r);
+        px = (double)x[r]; py = (double)y[r]; pz = (double)z[r];      // global or shared memory
     }
 };
 
@@ -266,37 +266,45 @@ __device__ bool hull_edge_listed(const int32_t *faces, int n_faces, int s, int t
     return __syncthreads_or(found) != 0;
 }
 
-// Flags the convex-hull vertices of the block's instance in vflag[0..m).  Returns the number of faces
-// (>= 4), or 0 when the cloud is flat (collinear / coplanar) or the wrapping did not close.
-__device__ int hull_vertices(const HullPts &P, int32_t *faces, int face_cap, uint8_t *vflag, int *s_cand)
+// First face of the hull: (b, a, p0) with a the lexicographic minimum, b the next vertex of the 2-D hull of the xy
+// projection, p0 across the reversed edge of the virtual vertical face.  False when the cloud is flat.
+__device__ bool hull_seed(const HullPts &P, int *s_cand, int &a, int &b, int &p0)
 {
-    for (int r = threadIdx.x; r < P.m; r += blockDim.x) vflag[r] = 0;
-    const int a = hull_lexmin(P, s_cand);
-    const int b = hull_next2d(P, a, s_cand);
-    if (b < 0) return 0;
+    a = hull_lexmin(P, s_cand);
+    b = hull_next2d(P, a, s_cand);
+    if (b < 0) return false;
     double ax, ay, az, bx, by, bz;
     P.get(a, ax, ay, az);
     P.get(b, bx, by, bz);
     HullEdge E;
-    // first face: across the reversed edge (b, a) of the virtual vertical face (a, b, a + (0,0,1))
     E.sx = bx; E.sy = by; E.sz = bz;
     E.ex = ax - bx; E.ey = ay - by; E.ez = az - bz;
     E.zx = E.ex; E.zy = E.ey; E.zz = E.ez + 1.0;
-    const int p0 = hull_wrap(P, E, b, a, s_cand);
-    if (p0 < 0) return 0;
-    {   // flat cloud: every point in the plane of the first face (exact test)
-        double px, py, pz;
-        P.get(p0, px, py, pz);
-        px -= bx; py -= by; pz -= bz;
-        const double nx = E.ey * pz - E.ez * py, ny = E.ez * px - E.ex * pz, nz = E.ex * py - E.ey * px;
-        int off = 0;
-        for (int r = threadIdx.x; r < P.m; r += blockDim.x) {
-            double qx, qy, qz;
-            P.get(r, qx, qy, qz);
-            off |= (nx * (qx - bx) + ny * (qy - by) + nz * (qz - bz)) != 0.0;
-        }
-        if (!__syncthreads_or(off)) return 0;
+    p0 = hull_wrap(P, E, b, a, s_cand);
+    if (p0 < 0) return false;
+    // flat cloud: every point in the plane of the first face (exact test)
+    double px, py, pz;
+    P.get(p0, px, py, pz);
+    px -= bx; py -= by; pz -= bz;
+    const double nx = E.ey * pz - E.ez * py, ny = E.ez * px - E.ex * pz, nz = E.ex * py - E.ey * px;
+    int off = 0;
+    for (int r = threadIdx.x; r < P.m; r += blockDim.x) {
+        double qx, qy, qz;
+        P.get(r, qx, qy, qz);
+        off |= (nx * (qx - bx) + ny * (qy - by) + nz * (qz - bz)) != 0.0;
     }
+    return __syncthreads_or(off) != 0;
+}
+
+// Flags the convex-hull vertices of the block's instance in vflag[0..m), one edge at a time with the whole block
+// (the fallback for clouds whose survivors do not fit shared memory).  Returns the number of faces
+// (>= 4), or 0 when the cloud is flat (collinear / coplanar) or the wrapping did not close.
+__device__ int hull_vertices(const HullPts &P, int32_t *faces, int face_cap, uint8_t *vflag, int *s_cand)
+{
+    for (int r = threadIdx.x; r < P.m; r += blockDim.x) vflag[r] = 0;
+    int a, b, p0;
+    if (!hull_seed(P, s_cand, a, b, p0)) return 0;
+    HullEdge E;
     int n_faces = 1;
     if (threadIdx.x == 0) {
         faces[0] = b; faces[1] = a; faces[2] = p0;
@@ -330,19 +338,393 @@ __device__ int hull_vertices(const HullPts &P, int32_t *faces, int face_cap, uin
     return n_faces;
 }
 
+// ------------------------------------------------------------------------------------------ one edge per WARP
+// The block-wide wrap above pays ~8 barriers and two reduction levels per face, and a hull has 10^2..10^3 faces.
+// With the points in shared memory every warp wraps its OWN open edge: the open edges sit in a queue, the
+// directed edges of the faces found so far in a hash set, both in shared memory.  A face is committed through
+// its canonical directed edge (the rotation that starts at its smallest vertex): whichever warp inserts that
+// edge first owns the face, so a face reached from two of its edges at the same time is counted once.
+constexpr int kEdgeTab = 8192;               // directed-edge hash set (open addressing), entries: key + 1
+constexpr int kEdgeMax = kEdgeTab * 3 / 4;
+constexpr int kQueueCap = 8192;
+
+struct WrapTables {
+    uint32_t etab[kEdgeTab];
+    uint32_t q_st[kQueueCap];                // (s << 16 | t) + 1, 0 = not yet written
+    uint16_t q_w[kQueueCap];                 // third vertex of the face the open edge borders
+    int tail, head, outstanding, n_faces, n_edges, fail;
+};
+
+__device__ __forceinline__ uint32_t edge_hash(uint32_t key) { return (key * 2654435761u) >> 19; }      // 13 bits
+
+// true when the directed edge was not in the set before
+__device__ bool edge_insert(WrapTables &W, uint32_t key)
+{
+    uint32_t h = edge_hash(key) & (kEdgeTab - 1);
+    for (int probe = 0; probe < kEdgeTab; ++probe) {
+        const uint32_t old = atomicCAS(&W.etab[h], 0u, key + 1u);
+        if (old == 0u) {
+            if (atomicAdd(&W.n_edges, 1) >= kEdgeMax) atomicExch(&W.fail, 1);
+            return true;
+        }
+        if (old == key + 1u) return false;
+        h = (h + 1) & (kEdgeTab - 1);
+    }
+    atomicExch(&W.fail, 1);
+    return false;
+}
+
+__device__ bool edge_present(WrapTables &W, uint32_t key)
+{
+    uint32_t h = edge_hash(key) & (kEdgeTab - 1);
+    for (int probe = 0; probe < kEdgeTab; ++probe) {
+        const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&W.etab[h]);
+        if (cur == 0u) return false;
+        if (cur == key + 1u) return true;
+        h = (h + 1) & (kEdgeTab - 1);
+    }
+    return false;
+}
+
+__device__ void queue_push(WrapTables &W, int s, int t, int w)
+{
+    atomicAdd(&W.outstanding, 1);
+    const int i = atomicAdd(&W.tail, 1);
+    if (i >= kQueueCap) { atomicExch(&W.fail, 1); atomicSub(&W.outstanding, 1); return; }
+    W.q_w[i] = (uint16_t)w;
+    __threadfence_block();
+    *reinterpret_cast<volatile uint32_t *>(&W.q_st[i]) = (((uint32_t)s << 16) | (uint32_t)t) + 1u;
+}
+
+// lane 0 only.  Commits face (s, t, p) unless it exists; pushes its still-open neighbours' edges.
+__device__ void face_commit(WrapTables &W, int s, int t, int p, uint8_t *vflag, int32_t *faces, int face_cap)
+{
+    int a = s, b = t, c = p;
+    if (b < a && b < c) { a = t; b = p; c = s; }
+    else if (c < a && c < b) { a = p; b = s; c = t; }
+    if (!edge_insert(W, ((uint32_t)a << 16) | (uint32_t)b)) return;           // another warp owns this face
+    const bool ok1 = edge_insert(W, ((uint32_t)b << 16) | (uint32_t)c);
+    const bool ok2 = edge_insert(W, ((uint32_t)c << 16) | (uint32_t)a);
+    if (!ok1 || !ok2) atomicExch(&W.fail, 2);                                 // a directed edge in two faces: not a hull
+    const int f = atomicAdd(&W.n_faces, 1);
+    if (faces) {
+        if (f < face_cap) { faces[3 * f] = a; faces[3 * f + 1] = b; faces[3 * f + 2] = c; }
+        else atomicExch(&W.fail, 1);
+    }
+    vflag[a] = 1; vflag[b] = 1; vflag[c] = 1;
+    if (!edge_present(W, ((uint32_t)b << 16) | (uint32_t)a)) queue_push(W, b, a, c);
+    if (!edge_present(W, ((uint32_t)c << 16) | (uint32_t)b)) queue_push(W, c, b, a);
+    if (!edge_present(W, ((uint32_t)a << 16) | (uint32_t)c)) queue_push(W, a, c, b);
+}
+
+// p such that no point lies outside the plane (S, T, p), found by ONE warp (-1: every point on the edge's line)
+__device__ int hull_wrap_warp(const HullPts &P, const HullEdge &E, int s, int t)
+{
+    const int lane = (int)lane_id();
+    int best = -1;
+    for (int r = lane; r < P.m; r += 32) {
+        if (r == s || r == t) continue;
+        if (best < 0) {
+            double wx, wy, wz;
+            P.get(r, wx, wy, wz);
+            wx -= E.sx; wy -= E.sy; wz -= E.sz;
+            const double nx = E.ey * wz - E.ez * wy, ny = E.ez * wx - E.ex * wz, nz = E.ex * wy - E.ey * wx;
+            if (nx * nx + ny * ny + nz * nz > 0.0) best = r;
+        } else if (hull_beats(P, E, best, r)) {
+            best = r;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other >= 0 && other != best && (best < 0 || hull_beats(P, E, best, other))) best = other;
+    }
+    return best;
+}
+
+// The hull of a point set that lives in shared memory (P.m <= 65535 local indices), all warps of the block
+// wrapping edges at once.  Flags the vertices in vflag[0..P.m); faces (optional) receives the face list.
+// Returns the number of faces, 0 for a flat cloud, -1 when the tables overflowed or the wrapping was
+// inconsistent (the caller falls back to the block-wide version).
+__device__ int hull_vertices_par(const HullPts &P, WrapTables &W, int32_t *faces, int face_cap, uint8_t *vflag, int *s_cand)
+{
+    for (int r = threadIdx.x; r < P.m; r += blockDim.x) vflag[r] = 0;
+    for (int k = threadIdx.x; k < kEdgeTab; k += blockDim.x) W.etab[k] = 0u;
+    for (int k = threadIdx.x; k < kQueueCap; k += blockDim.x) W.q_st[k] = 0u;
+    if (threadIdx.x == 0) { W.tail = W.head = W.outstanding = W.n_faces = W.n_edges = W.fail = 0; }
+    int a, b, p0;
+    if (!hull_seed(P, s_cand, a, b, p0)) return 0;            // (barriers inside: the tables are clear past this point)
+    if (threadIdx.x == 0) face_commit(W, b, a, p0, vflag, faces, face_cap);
+    __syncthreads();
+    const int lane = (int)lane_id();
+    for (int iter = 0;; ++iter) {
+        // lane 0 takes the next open edge: slot index, -1 = nothing queued right now, -2 = all done (or failed)
+        int slot = -1;
+        if (iter > (1 << 21) && lane == 0) atomicExch(&W.fail, 1);            // never spin forever
+        if (lane == 0) {
+            if (*reinterpret_cast<volatile int *>(&W.fail)) slot = -2;
+            else {
+                const int h = *reinterpret_cast<volatile int *>(&W.head);
+                const int tl = min(*reinterpret_cast<volatile int *>(&W.tail), kQueueCap);
+                if (h < tl) {
+                    if (atomicCAS(&W.head, h, h + 1) == h) slot = h;
+                } else if (*reinterpret_cast<volatile int *>(&W.outstanding) == 0) slot = -2;
+            }
+        }
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot == -2) break;
+        if (slot == -1) { __nanosleep(100); continue; }
+        uint32_t key = 0;
+        int w = 0;
+        if (lane == 0) {
+            int spin = 0;
+            while ((key = *reinterpret_cast<volatile uint32_t *>(&W.q_st[slot])) == 0u && ++spin < (1 << 24)) {}     // the pusher writes it last
+            if (key == 0u) { atomicExch(&W.fail, 1); key = 1u; }
+            key -= 1u;
+            w = (int)*reinterpret_cast<volatile uint16_t *>(&W.q_w[slot]);
+            if (edge_present(W, key)) key = 0xffffffffu;                                            // closed meanwhile
+        }
+        key = __shfl_sync(0xffffffffu, key, 0);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (key != 0xffffffffu) {
+            const int es = (int)(key >> 16), et = (int)(key & 0xffffu);
+            double sx, sy, sz, tx, ty, tz, wx, wy, wz;
+            P.get(es, sx, sy, sz);
+            P.get(et, tx, ty, tz);
+            P.get(w, wx, wy, wz);
+            HullEdge E;
+            E.sx = sx; E.sy = sy; E.sz = sz;
+            E.ex = tx - sx; E.ey = ty - sy; E.ez = tz - sz;
+            E.zx = wx - sx; E.zy = wy - sy; E.zz = wz - sz;
+            const int p = hull_wrap_warp(P, E, es, et);
+            if (lane == 0) {
+                if (p < 0 || p == w) atomicExch(&W.fail, 3);
+                else face_commit(W, es, et, p, vflag, faces, face_cap);
+            }
+        }
+        if (lane == 0) { __threadfence_block(); atomicSub(&W.outstanding, 1); }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (W.fail) return W.fail == 3 ? 0 : -1;          // 3: a wrap came back flat (degenerate input) -> the reference's fallback box
+    return W.n_faces;
+}
+
+// ------------------------------------------------------------------------------------------ prefilter
+// Gift wrapping costs (faces x points) determinant evaluations, and a LiDAR segment has 10^3..10^4 points of
+// which a few per cent are hull vertices.  So first: the extreme points of the cloud along up to 256 fixed
+// directions (a Fibonacci sphere; fp32 dot products - ANY subset of the input works), their hull by the same
+// gift wrapping (<= 256 points: cheap), and every point strictly inside that inner polytope (fp64 plane
+// tests with a 2^-40 relative guard band) is dropped: it cannot be a vertex of the full hull.  ~10 % of a
+// segment survives; the survivors' coordinates move to shared memory and are wrapped there.  A cloud
+// whose coarse hull is flat, whose coarse face count is inconsistent, or whose survivors do not fit falls
+// back to wrapping every point from global memory.
+constexpr int kHullDirs = 256;
+constexpr int kHullSurvCap = 4096;
+constexpr int kHullDirect = 768;             // clouds this small are wrapped directly (in shared memory)
+constexpr int kCoarseFaceCap = 2 * kHullDirs;
+
+struct HullShared {
+    float sx[kHullSurvCap], sy[kHullSurvCap], sz[kHullSurvCap];
+    int32_t sorig[kHullSurvCap];
+    uint8_t sflag[kHullSurvCap];
+    double plane[kCoarseFaceCap][4];
+    int32_t cfaces[3 * kCoarseFaceCap];
+    float dirs[kHullDirs][3];
+    int32_t ext[kHullDirs];
+    int32_t wsum[kHullThreads / 32];
+    int32_t count;
+    WrapTables W;
+};
+
+// Loads the whole cloud (m <= kHullSurvCap) into shared memory, identity index map.
+__device__ void hull_load_all(HullShared &S, const float *sx, const float *sy, const float *sz, int m)
+{
+    for (int r = threadIdx.x; r < m; r += blockDim.x) {
+        S.sx[r] = sx[r]; S.sy[r] = sy[r]; S.sz[r] = sz[r]; S.sorig[r] = r;
+    }
+    __syncthreads();
+}
+
+// Extreme points along n_dir directions -> S.ext[0..n_dir)
+__device__ void hull_extremes(HullShared &S, const float *sx, const float *sy, const float *sz, int m, int n_dir)
+{
+    __shared__ float s_bv[kHullThreads / 32][8];
+    __shared__ int s_bi[kHullThreads / 32][8];
+    for (int k = threadIdx.x; k < n_dir; k += blockDim.x) {
+        const float c = 1.0f - 2.0f * ((float)k + 0.5f) / (float)n_dir;
+        const float sn = sqrtf(fmaxf(1.0f - c * c, 0.0f));
+        float st, ct;
+        sincosf(2.39996322972865332f * (float)k, &st, &ct);
+        S.dirs[k][0] = ct * sn; S.dirs[k][1] = st * sn; S.dirs[k][2] = c;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = (int)lane_id();
+    for (int d0 = 0; d0 < n_dir; d0 += 8) {
+        float bv[8];
+        int bi[8];
+        float dx[8], dy[8], dz[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            bv[k] = -INFINITY; bi[k] = -1;
+            const int d = min(d0 + k, n_dir - 1);
+            dx[k] = S.dirs[d][0]; dy[k] = S.dirs[d][1]; dz[k] = S.dirs[d][2];
+        }
+        for (int r = threadIdx.x; r < m; r += blockDim.x) {
+            const float x = sx[r], y = sy[r], z = sz[r];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float v = dx[k] * x + dy[k] * y + dz[k] * z;
+                if (v > bv[k]) { bv[k] = v; bi[k] = r; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv[k], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi[k], o);
+                if (ov > bv[k] || (ov == bv[k] && oi >= 0 && (bi[k] < 0 || oi < bi[k]))) { bv[k] = ov; bi[k] = oi; }
+            }
+            if (lane == 0) { s_bv[warp][k] = bv[k]; s_bi[warp][k] = bi[k]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 8 && d0 + (int)threadIdx.x < n_dir) {
+            float v = -INFINITY;
+            int idx = -1;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+                if (s_bv[w][threadIdx.x] > v || (s_bv[w][threadIdx.x] == v && s_bi[w][threadIdx.x] >= 0 && (idx < 0 || s_bi[w][threadIdx.x] < idx))) {
+                    v = s_bv[w][threadIdx.x]; idx = s_bi[w][threadIdx.x];
+                }
+            S.ext[d0 + threadIdx.x] = idx;
+        }
+        __syncthreads();
+    }
+}
+
+// Flags of the hull vertices into vflag[0..m).  Returns (faces, vertices) of the hull, faces = 0 when flat.
+__device__ int hull_vertices_filtered(HullShared &S, const float *sx, const float *sy, const float *sz, int m,
+                                      int32_t *faces_ws, uint8_t *vflag, int *s_cand)
+{
+    for (int r = threadIdx.x; r < m; r += blockDim.x) vflag[r] = 0;
+    int ns = -1;                                  // survivors in shared memory (-1: wrap every point from global memory)
+    if (m <= kHullDirect) {
+        hull_load_all(S, sx, sy, sz, m);
+        ns = m;
+    } else {
+        int n_dir = min(kHullDirs, max(32, m / 32)) & ~7;
+        hull_extremes(S, sx, sy, sz, m, n_dir);
+        // distinct extreme points, in direction order -> the coarse set in S.sx/sy/sz[0..nc)
+        if (threadIdx.x == 0) S.count = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int nc = 0;
+            for (int k = 0; k < n_dir; ++k) {
+                const int e = S.ext[k];
+                bool dup = e < 0;
+                for (int j = 0; j < nc && !dup; ++j) dup = S.sorig[j] == e;
+                if (!dup) { S.sorig[nc] = e; S.sx[nc] = sx[e]; S.sy[nc] = sy[e]; S.sz[nc] = sz[e]; ++nc; }
+            }
+            S.count = nc;
+        }
+        __syncthreads();
+        const int nc = S.count;
+        HullPts C{S.sx, S.sy, S.sz, nc};
+        const int nf = nc >= 4 ? hull_vertices_par(C, S.W, S.cfaces, kCoarseFaceCap, S.sflag, s_cand) : 0;
+        __syncthreads();
+        bool usable = nf >= 4;
+        if (usable) {                             // Euler check of the coarse hull, then its planes
+            int v = 0;
+            for (int r = threadIdx.x; r < nc; r += blockDim.x) v += S.sflag[r];
+            int tot = 0;
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
+            if (lane_id() == 0) S.wsum[threadIdx.x >> 5] = v;
+            __syncthreads();
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += S.wsum[w];
+            usable = nf == 2 * tot - 4;
+            __syncthreads();
+        }
+        if (usable) {
+            for (int f = threadIdx.x; f < nf; f += blockDim.x) {
+                const int a = S.cfaces[3 * f], b = S.cfaces[3 * f + 1], c = S.cfaces[3 * f + 2];
+                const double ax = S.sx[a], ay = S.sy[a], az = S.sz[a];
+                const double ux = (double)S.sx[b] - ax, uy = (double)S.sy[b] - ay, uz = (double)S.sz[b] - az;
+                const double vx = (double)S.sx[c] - ax, vy = (double)S.sy[c] - ay, vz = (double)S.sz[c] - az;
+                const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;     // outward
+                const double off = -(nx * ax + ny * ay + nz * az);
+                // guard band: |rounding of n.p + off| <= ~8 ulp of |n|_1 * max|coordinate|; 2^-40 is 10^3 times that
+                const double R = fabs(ax) + fabs(ay) + fabs(az) + fabs(ux) + fabs(uy) + fabs(uz) + fabs(vx) + fabs(vy) + fabs(vz);
+                S.plane[f][0] = nx; S.plane[f][1] = ny; S.plane[f][2] = nz;
+                S.plane[f][3] = off + (fabs(nx) + fabs(ny) + fabs(nz)) * R * 0x1p-40;                   // inside iff n.p + this < 0
+            }
+            __syncthreads();
+            // survivors, in index order (ballot ranks + a scan of the warp totals per chunk of blockDim points)
+            int base = 0;
+            bool overflow = false;
+            const int warp = threadIdx.x >> 5, lane = (int)lane_id(), nw = (int)(blockDim.x >> 5);
+            for (int c0 = 0; c0 < m; c0 += blockDim.x) {
+                const int r = c0 + threadIdx.x;
+                bool keep = false;
+                float x = 0.f, y = 0.f, z = 0.f;
+                if (r < m) {
+                    x = sx[r]; y = sy[r]; z = sz[r];
+                    const double px = x, py = y, pz = z;
+                    for (int f = 0; f < nf; ++f)
+                        if (!(S.plane[f][0] * px + S.plane[f][1] * py + S.plane[f][2] * pz + S.plane[f][3] < 0.0)) { keep = true; break; }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (lane == 0) S.wsum[warp] = __popc(bal);
+                __syncthreads();
+                int before = 0, total = 0;
+                for (int w = 0; w < nw; ++w) { if (w < warp) before += S.wsum[w]; total += S.wsum[w]; }
+                if (base + total > kHullSurvCap) overflow = true;
+                else if (keep) {
+                    const int at = base + before + __popc(bal & lanemask_lt());
+                    S.sx[at] = x; S.sy[at] = y; S.sz[at] = z; S.sorig[at] = r;
+                }
+                base += total;
+                __syncthreads();
+                if (overflow) break;
+            }
+            if (!overflow) ns = base;
+        }
+        if (ns < 0 && m <= kHullSurvCap) {        // no usable coarse hull, but the cloud fits: wrap it in shared memory
+            __syncthreads();
+            hull_load_all(S, sx, sy, sz, m);
+            ns = m;
+        }
+    }
+    __syncthreads();
+    if (ns < 0) {                                 // fallback: every point, from global memory
+        HullPts P{sx, sy, sz, m};
+        return hull_vertices(P, faces_ws, 2 * m, vflag, s_cand);
+    }
+    HullPts P{S.sx, S.sy, S.sz, ns};
+    int n_faces = hull_vertices_par(P, S.W, nullptr, 0, S.sflag, s_cand);
+    __syncthreads();
+    if (n_faces < 0) n_faces = hull_vertices(P, faces_ws, 2 * m, S.sflag, s_cand);       // tables overflowed: one edge at a time
+    __syncthreads();
+    if (n_faces > 0)
+        for (int r = threadIdx.x; r < ns; r += blockDim.x)
+            if (S.sflag[r]) vflag[S.sorig[r]] = 1;
+    __syncthreads();
+    return n_faces;
+}
+
 // ------------------------------------------------------------------------------------------ the box
 // mode 0: hull vertices (open3d); mode 1: all member points (round 1's estimator, kept for comparison)
-__global__ void __launch_bounds__(kHullThreads)
+__global__ void __launch_bounds__(kHullThreads, 1)
 k_hull_obb(const float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *__restrict__ seg_off, int min_pts, int mode,
-           int32_t *__restrict__ hull_ws, float *__restrict__ obb, int32_t *__restrict__ hull_info,
-           const int32_t *__restrict__ errflags)
+           const int32_t *__restrict__ order, int32_t *__restrict__ hull_ws, float *__restrict__ obb,
+           int32_t *__restrict__ hull_info, const int32_t *__restrict__ errflags)
 {
     __shared__ double s_red[32];
     __shared__ float s_redf[32];
     __shared__ int s_cand[33];
     __shared__ double s_R[3][3];
     __shared__ double s_mean[3];
-    const int i = blockIdx.x;
+    const int i = order ? order[blockIdx.x] : (int)blockIdx.x;       // largest instances first (the medoid's schedule)
     float *out = obb + (size_t)i * 16;
     const float nanv = __int_as_float(0x7fc00000);
     const int o = seg_off[i], m = seg_off[i + 1] - o;
@@ -355,8 +737,9 @@ k_hull_obb(const float *__restrict__ seg_xyzw, int64_t seg_cap, const int32_t *_
     uint8_t *vflag = reinterpret_cast<uint8_t *>(hull_ws + 6 * seg_cap) + o;
     int n_faces = -1;
     if (mode == 0) {
-        HullPts P{sx, sy, sz, m};
-        n_faces = hull_vertices(P, hull_ws + 6 * (int64_t)o, 2 * m, vflag, s_cand);
+        extern __shared__ __align__(16) unsigned char s_dyn[];
+        HullShared &S = *reinterpret_cast<HullShared *>(s_dyn);
+        n_faces = hull_vertices_filtered(S, sx, sy, sz, m, hull_ws + 6 * (int64_t)o, vflag, s_cand);
         __syncthreads();
         if (n_faces == 0) {       // kitti:1483-1484: bbox = [pts3d[0], [1,1,1], identity] -> yaw 0
             if (threadIdx.x == 0) {
@@ -488,15 +871,20 @@ using namespace cm3d;
 extern "C" int64_t cm3d_hull_obb_ws_words(int64_t seg_cap) { return 6 * seg_cap + (seg_cap + 3) / 4 + 4; }
 
 extern "C" int cm3d_hull_obb(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
-                             int min_pts, int mode, int32_t *hull_ws, int64_t hull_ws_words, float *obb,
-                             int32_t *hull_info, const int32_t *errflags, void *stream)
+                             int min_pts, int mode, const int32_t *order, int32_t *hull_ws, int64_t hull_ws_words,
+                             float *obb, int32_t *hull_info, const int32_t *errflags, void *stream)
 {
     if (n_inst_total < 0 || seg_cap < 0 || (mode != 0 && mode != 1)) return CM3D_EINVAL;
     if (n_inst_total == 0) return CM3D_OK;
     if (!seg_xyzw || !seg_off || !obb || !errflags) return CM3D_EINVAL;
     if (mode == 0 && (!hull_ws || hull_ws_words < cm3d_hull_obb_ws_words(seg_cap))) return CM3D_EINVAL;
-    k_hull_obb<<<n_inst_total, kHullThreads, 0, (cudaStream_t)stream>>>(seg_xyzw, seg_cap, seg_off, min_pts, mode, hull_ws,
-                                                                        obb, hull_info, errflags);
+    const size_t smem = mode == 0 ? sizeof(HullShared) : 0;
+    if (smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_hull_obb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -(1000 + (int)e);
+    }
+    k_hull_obb<<<n_inst_total, kHullThreads, smem, (cudaStream_t)stream>>>(seg_xyzw, seg_cap, seg_off, min_pts, mode, order,
+                                                                           hull_ws, obb, hull_info, errflags);
     CM3D_LAUNCH_CHECK();
     return CM3D_OK;
 }

@@ -360,31 +360,53 @@ class Lifter:
             o("seg_off")[:I + 1].copy_(seg_off2[:I + 1])
             seg_point_idx, seg_xyzw = seg_point_idx2, seg_xyzw2
 
-        # ---- second phase (medoid, boxes): same stream, or the lifter's medoid stream behind an event
+        # ---- second phase (medoid, box search): same stream, or the lifter's medoid stream behind an event
         front = torch.cuda.current_stream(dev)
         phase2 = None
+        st2 = st
         if overlap:
             if self._med_stream is None:
                 self._med_stream = torch.cuda.Stream(dev)
             phase2 = self._med_stream
             ev = torch.cuda.Event()
-            ev.record(front)
+            ev.record(front)                         # the segments are gathered: the medoid may start
             phase2.wait_event(ev)
             for t in (out, seg_point_idx, seg_xyzw, medoid_best, item_inst):
                 t.record_stream(phase2)              # allocated on the front stream, read / written on the other one
-            st = ctypes.c_void_p(phase2.cuda_stream)
-        with torch.cuda.stream(phase2 if phase2 is not None else front):
-            do = self._run_phase2(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, medoid_best, item_inst, st,
-                                  want_col_sums, do_medoid, want_obb, box_search)
+            st2 = ctypes.c_void_p(phase2.cuda_stream)
+
+        # ---- KITTI: open3d's box of the hull vertices + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479).
+        # Stays on the front stream: in overlap mode it runs NEXT TO this batch's medoid (both only read the segments).
+        obb = hull_info = ev_hull = None
+        if want_obb is None:
+            want_obb = pb.any_kitti
+        if want_obb and I:
+            obb = torch.empty(I * 16, dtype=torch.float32, device=dev)
+            hull_info = torch.empty(I, **i32)
+            ws_words = int(N.load().cm3d_hull_obb_ws_words(seg_cap)) if self.obb_mode == 0 else 1
+            hull_ws = torch.empty(ws_words, **i32)
+            self._call("hull_obb", "cm3d_hull_obb", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, 4, int(self.obb_mode),
+                       _ptr(item_inst), _ptr(hull_ws), ws_words, _ptr(obb), _ptr(hull_info), _ptr(o("errflags")), st)
+            self.launches += 1
             if phase2 is not None:
+                ev_hull = torch.cuda.Event()
+                ev_hull.record(front)
+        self.last_hull_info = hull_info
+
+        with torch.cuda.stream(phase2 if phase2 is not None else front):
+            do = self._run_phase2(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, medoid_best, item_inst, st2,
+                                  want_col_sums, do_medoid, box_search)
+            if phase2 is not None:
+                if ev_hull is not None:
+                    phase2.wait_event(ev_hull)       # `done` covers the boxes too
                 do.done = torch.cuda.Event()
                 do.done.record(phase2)
-        do.xyzw, do.tile_cnt, do.tile_prefix, do.pix, do.hits, do.bits, do.bbox, do.seg_off_raw = \
-            xyzw, tile_cnt, tile_prefix, pix, hits, bits, bbox, seg_off_raw
+        do.xyzw, do.tile_cnt, do.tile_prefix, do.pix, do.hits, do.bits, do.bbox, do.seg_off_raw, do.obb = \
+            xyzw, tile_cnt, tile_prefix, pix, hits, bits, bbox, seg_off_raw, obb
         return do
 
     def _run_phase2(self, db, out, lay, seg_cap, seg_point_idx, seg_xyzw, medoid_best, item_inst, st,
-                    want_col_sums, do_medoid, want_obb, box_search) -> DeviceOutputs:
+                    want_col_sums, do_medoid, box_search) -> DeviceOutputs:
         pb, dev = db.pb, self.device
         I = pb.n_inst
         i32 = dict(dtype=torch.int32, device=dev)
@@ -413,19 +435,6 @@ class Lifter:
             self.launches += (6 if self.screen_flags & 1 else (8 if self.screen_flags & 2 else 9)) if screen else 3
         self.last_screen_stats = screen_stats
         self.last_screen_modes = screen_min[I:4 * I] if (do_medoid and I and screen_min is not None) else None
-        # ---- KITTI: open3d's box of the hull vertices + yaw (kitti/2d_to_3d.py:855-876,1524; M <= 3 skipped, :1479)
-        obb = hull_info = None
-        if want_obb is None:
-            want_obb = pb.any_kitti
-        if want_obb and I:
-            obb = torch.empty(I * 16, dtype=torch.float32, device=dev)
-            hull_info = torch.empty(I, **i32)
-            ws_words = int(N.load().cm3d_hull_obb_ws_words(seg_cap)) if self.obb_mode == 0 else 1
-            hull_ws = torch.empty(ws_words, **i32)
-            self._call("hull_obb", "cm3d_hull_obb", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, 4, int(self.obb_mode),
-                       _ptr(hull_ws), ws_words, _ptr(obb), _ptr(hull_info), _ptr(o("errflags")), st)
-            self.launches += 1
-        self.last_hull_info = hull_info
         box = None
         if box_search and I:
             kitti_flags = {f == "kitti" for f in pb.frame_datasets}
@@ -437,7 +446,7 @@ class Lifter:
                        int(box_search), 1, _ptr(box), _ptr(o("errflags")), st)
             self.launches += 1
         return DeviceOutputs(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, None, None, None,
-                             None, col_sums, None, None, None, obb, box, None)
+                             None, col_sums, None, None, None, None, box, None)
 
     # ------------------------------------------------------------------ device -> host
     @_on_device

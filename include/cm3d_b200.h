@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 11
+#define CM3D_ABI_VERSION 12
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
@@ -234,11 +234,12 @@ int cm3d_medoid_items(int m, int min_pts);
  * mode 1 = PCA of all member points (round 1's estimator; diagnostics only).  hull_ws: scratch of
  * cm3d_hull_obb_ws_words(seg_cap) int32 words (mode 0).  hull_info (optional, n_inst_total ints):
  * hull vertex count; -1 = flat / fallback; -(count+1) = wrapping closed with an inconsistent face
- * count (exactly degenerate input); 0 = skipped. */
+ * count (exactly degenerate input); 0 = skipped.  order (optional, n_inst_total ints): instance handled by
+ * block b - cm3d_scan_segments' item_inst lists the instances largest first, which keeps the launch's tail short. */
 int64_t cm3d_hull_obb_ws_words(int64_t seg_cap);
 int cm3d_hull_obb(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off, int n_inst_total,
-                  int min_pts, int mode, int32_t *hull_ws, int64_t hull_ws_words, float *obb,
-                  int32_t *hull_info, const int32_t *errflags, void *stream);
+                  int min_pts, int mode, const int32_t *order, int32_t *hull_ws, int64_t hull_ws_words,
+                  float *obb, int32_t *hull_info, const int32_t *errflags, void *stream);
 
 /* ---- default-off extensions (north star (3)/(4); never executed by the reference: PARITY UNPINNED) ---- */
 

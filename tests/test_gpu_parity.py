@@ -500,7 +500,7 @@ def test_hull_obb_flat_and_tiny_clouds_take_the_reference_fallback(lifter):
     words = int(N.load().cm3d_hull_obb_ws_words(seg_cap))
     ws = torch.empty(words, dtype=torch.int32, device="cuda")
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    N.call("cm3d_hull_obb", p(xyzw), seg_cap, p(seg_off), I, 4, 0, p(ws), words, p(obb), p(info), p(err),
+    N.call("cm3d_hull_obb", p(xyzw), seg_cap, p(seg_off), I, 4, 0, None, p(ws), words, p(obb), p(info), p(err),
            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     obb, info = obb.cpu().numpy().reshape(I, 16), info.cpu().numpy()
     for k in range(3):                                              # flat / collinear / single point
