@@ -847,7 +847,8 @@ k_compact(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *__rest
                         const int64_t dst = (int64_t)kb + s_pc[k * kGroups + r * (kBlock / 32) + warp] + __popc(bal & lanemask_lt());
                         if (dst < seg_cap) {
                             seg_point_idx[dst] = tp0 + r * kBlock + threadIdx.x;
-                            sx[dst] = px[r]; sy[dst] = py[r]; sz[dst] = pz[r]; sw[dst] = pw[r];
+                            sx[dst] = px[r]; sy[dst] = py[r]; sz[dst] = pz[r];
+                            if (fourth) sw[dst] = pw[r];
                         }
                     }
                 }
@@ -903,7 +904,8 @@ k_compact(const float *__restrict__ xyzw, int64_t n_slots, const int32_t *__rest
                     const int64_t dst = (int64_t)s_base[j] + s_gc[g * ni + j] + __popc(m & lanemask_lt());
                     if (dst < seg_cap) {
                         seg_point_idx[dst] = tp + s;
-                        sx[dst] = x; sy[dst] = y; sz[dst] = z; sw[dst] = w;
+                        sx[dst] = x; sy[dst] = y; sz[dst] = z;
+                        if (fourth) sw[dst] = w;
                     }
                 }
                 if (mine == jmin) ph.pop();
