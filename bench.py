@@ -34,13 +34,13 @@ MASK_INPUT = "COCO counts strings (pycocotools format), decoded on the GPU"
 # BASELINE.json configs.  `gen` is the synthetic generator's config name (c5 = independent C2-shaped frames),
 # `batch` the frames per GPU and launch sequence, `stream` the DISTINCT frames per GPU of the streaming legs.
 CONFIGS = {
-    "c2": dict(gen="c5", batch=64, stream=1024, cycles=8,
+    "c2": dict(gen="c5", batch=64, stream=1024, stream_total=8192,
                workload="C2: nuScenes-shaped 10 sweeps x 34,720 pts (~347k pts) x 6 cams 1024x576 masks x 50 instances per frame"),
-    "c1": dict(gen="c1", batch=64, stream=512, cycles=16,
+    "c1": dict(gen="c1", batch=64, stream=512, stream_total=32768,
                workload="C1: nuScenes-shaped single sample, 1 sweep (~34.7k pts) x 6 cams 1024x576 masks x 20 instances per frame"),
-    "c3": dict(gen="c3", batch=32, stream=256, cycles=8,
+    "c3": dict(gen="c3", batch=32, stream=256, stream_total=8192,
                workload="C3: KITTI-shaped 64-beam (~120k pts) x 1 cam, 1024x309 masks x 15 instances per frame"),
-    "c4": dict(gen="c4", batch=16, stream=128, cycles=8,
+    "c4": dict(gen="c4", batch=16, stream=128, stream_total=8192,
                workload="C4: Waymo-shaped top LiDAR (~180k pts) x 5 cams, 1024x683 / 1024x473 masks x 80 instances per frame"),
 }
 
@@ -434,15 +434,16 @@ def run_ours(args, rank, world, local_rank):
         # measured on the 16-vCPU box: 6 packer threads feed the GPU (3.8 k frames/s); 8 or 12 slow the launching thread down
         pw = max(2, min(args.pack_workers or 6, (os.cpu_count() or 2) // max(world, 1) - 1))
         fs_kw = dict(batch_frames=args.stream_batch, pack_workers=pw)
-        for _ in lifter.lift_frame_stream(iter(frames[:min(len(frames), 8 * 32)]), **fs_kw):     # also fills the pinned-buffer pool
+        import itertools
+        warm = max(16 * args.stream_batch, 256)                 # fills the pinned-buffer pool and the allocator's size classes
+        for _ in lifter.lift_frame_stream(itertools.islice(itertools.cycle(frames), warm), **fs_kw):
             pass
         barrier()
-        cycles = max(1, args.stream_cycles or cfg["cycles"])
+        cycles = max(1, args.stream_cycles or -(-cfg["stream_total"] // n_stream))
         lifter.stream_stats.clear()
         r0 = lifter.cap_retries
         t0 = time.perf_counter()
         n_fs = n_boxes = 0
-        import itertools
         for res in lifter.lift_frame_stream(itertools.chain.from_iterable(frames for _ in range(cycles)), **fs_kw):     # ONE stream
             n_fs += len(res)
             n_boxes += sum(int((r.medoid_local >= 0).sum()) for r in res)

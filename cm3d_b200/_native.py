@@ -68,10 +68,18 @@ def load():
     v = lib.cm3d_abi_version()
     if v != ABI_VERSION:
         raise Cm3dError(f"libcm3d_b200.so has ABI {v}, python side expects {ABI_VERSION}: rebuild")
+    # Kernel launches return in microseconds: they are bound through PyDLL, which keeps the GIL, so the launching
+    # thread does not queue behind the packer threads' Python sections a dozen times per batch.  The host packer
+    # (cm3d_pack_*: milliseconds of memcpy) stays on CDLL, which releases it.
+    pylib = ctypes.PyDLL(LIB_PATH)
     for name, args in PROTOTYPES.items():
-        fn = getattr(lib, name)
-        fn.restype = ctypes.c_int
-        fn.argtypes = args
+        for handle in (lib, pylib):
+            fn = getattr(handle, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = args
+    for name in PROTOTYPES:
+        if not name.startswith("cm3d_pack_"):
+            setattr(lib, name, getattr(pylib, name))
     _lib = lib
     return lib
 

@@ -130,6 +130,17 @@ def prefetch_map(fn, items, workers: int = 8, depth: int = 0):
             yield pending.popleft().result()
 
 
+def _round_up(n: int) -> int:
+    """n rounded up to 1, 1.125, ... 1.875 times a power of two (above 64 Ki): the workspace sizes of a stream
+    vary from batch to batch (mask sizes, member counts), and a caching allocator only reuses a block
+    for a request that is not larger - a handful of size classes keeps cudaMalloc out of the steady state."""
+    n = int(n)
+    if n < (1 << 16):
+        return n
+    q = 1 << (n.bit_length() - 4)
+    return (n + q - 1) // q * q
+
+
 def _on_device(fn):
     """Run a Lifter method with the lifter's GPU as the current CUDA device (generators included)."""
     import functools
@@ -189,6 +200,11 @@ class Lifter:
         self.timing = None          # dict label -> [(start_event, end_event)] when bench.py profiles
         self.obb_mode = 0           # KITTI box: 0 = hull vertices (open3d's algorithm), 1 = all member points (diagnostics)
         self.last_hull_info = None  # device int32[I]: hull vertex count per instance (-1: flat cloud -> the reference's fallback box)
+
+    def _buf(self, n, dtype=torch.int32):
+        """Uninitialised device buffer of n elements, from an allocation of a rounded-up size class."""
+        n = max(int(n), 1)
+        return torch.empty(_round_up(n), dtype=dtype, device=self.device)[:n]
 
     def _call(self, label: str, name: str, *args):
         """One C-ABI call; with `self.timing` set, bracketed by CUDA events on the launch stream."""
@@ -261,7 +277,7 @@ class Lifter:
             # largest ratio seen (+5 %); a batch that does not fit is rerun with its exact size (check_flags)
             factor = self.seg_factor if self._seg_ratio is None else min(self.seg_factor, 1.5 * self._seg_ratio + 0.05)
             seg_cap = int(factor * pb.n_raw_points) + 1024
-        seg_cap = (int(seg_cap) + 3) & ~3
+        seg_cap = _round_up((int(seg_cap) + 3) & ~3) if overlap else (int(seg_cap) + 3) & ~3     # streams: few distinct sizes
         i32 = dict(dtype=torch.int32, device=dev)
         lay = self._out_layout(F, I)
         out = torch.zeros(lay["_words"], **i32)
@@ -271,9 +287,9 @@ class Lifter:
             return out[a:a + max(n, 1)]
 
         # ---- masks -> eroded bit planes (+ bbox)
-        bits_raw = torch.empty(max(pb.bits_words, 1), **i32)
-        bits = torch.empty(max(pb.bits_words, 1), **i32)
-        bbox = torch.empty(max(I, 1) * 4, **i32)
+        bits_raw = self._buf(max(pb.bits_words, 1))
+        bits = self._buf(max(pb.bits_words, 1))
+        bbox = self._buf(max(I, 1) * 4)
         inst_desc = db.tab("inst_desc")
         row_range = None
         if I:
@@ -285,11 +301,11 @@ class Lifter:
                 bits_raw.zero_()
                 runs = db.mask
                 if pb.masks_kind == "rle_str":      # pycocotools counts strings -> run lengths on the device
-                    runs = torch.empty(max(db.mask.numel(), 1), **i32)
+                    runs = self._buf(max(db.mask.numel(), 1))
                     self._call("masks_decode", "cm3d_masks_decode_counts", _ptr(db.mask), _ptr(db.mask_off), I, _ptr(runs), st)
                     self.launches += 1
-                run_start = torch.empty(max(runs.numel(), 1), **i32)
-                row_range = torch.empty(2 * I, **i32)
+                run_start = self._buf(max(runs.numel(), 1))
+                row_range = self._buf(2 * I)
                 self._call("masks_rle", "cm3d_masks_fill_rle", _ptr(runs), _ptr(db.mask_off), _ptr(run_start), _ptr(inst_desc),
                        I, pb.max_runs, _ptr(bits_raw), _ptr(row_range), _ptr(o("errflags")), st)
                 self.launches += 2              # k_rle_prefix, k_rle_fill (torch's zero fill of the planes is not ours)
@@ -297,25 +313,25 @@ class Lifter:
                        pb.max_words, _ptr(bits), _ptr(bbox), st)
             self.launches += 2
 
-        vcam_grid = torch.empty(max(pb.grid_words, 1), **i32)
+        vcam_grid = self._buf(max(pb.grid_words, 1))
         if I:
             self._call("vcam_grid", "cm3d_build_vcam_grid", _ptr(db.tab("vcam_desc")), pb.n_vcams, pb.max_cells,
                        _ptr(db.tab("frame_desc")), _ptr(db.tab("cam_inst_list")), _ptr(bbox), _ptr(vcam_grid), st)
             self.launches += 1
 
         # ---- sweeps -> aggregated cloud
-        xyzw = torch.empty(4 * n_slots, dtype=torch.float32, device=dev)
-        tile_cnt = torch.empty(max(T, 1), **i32)
-        tile_prefix = torch.empty(max(T, 1), **i32)
+        xyzw = self._buf(4 * n_slots, torch.float32)
+        tile_cnt = self._buf(max(T, 1))
+        tile_prefix = self._buf(max(T, 1))
         self._call("aggregate", "cm3d_aggregate_sweeps", _ptr(db.raw), _ptr(db.tab("tile_sweep")), T, _ptr(db.tab("sweep_desc")),
                _ptr(db.tab("frame_desc")), _ptr(db.tab("chains")), _ptr(xyzw), _ptr(tile_cnt), st)
         self.launches += 1 if T else 0
 
         # ---- projection + membership (count pass)
-        hits = torch.empty(n_slots, **i32)
-        tile_inst_cnt = torch.empty(max(pb.cnt_total, 1), dtype=torch.int16, device=dev)
-        tile_inst_base = torch.empty(max(pb.cnt_total, 1), **i32)
-        pix = torch.empty(16 * n_slots, **i32) if want_pix else None
+        hits = self._buf(n_slots)
+        tile_inst_cnt = self._buf(max(pb.cnt_total, 1), torch.int16)
+        tile_inst_base = self._buf(max(pb.cnt_total, 1))
+        pix = self._buf(16 * n_slots) if want_pix else None
         self._call("project_count", "cm3d_project_membership", _ptr(xyzw), _ptr(tile_cnt), _ptr(db.tab("tile_sweep")), T,
                _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
                _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
@@ -323,15 +339,15 @@ class Lifter:
         self.launches += 1 if T else 0
 
         # ---- scans, ordered compaction + gather
-        medoid_best = torch.empty(max(I, 1), dtype=torch.int64, device=dev)
-        item_inst = torch.empty(max(I, 1), **i32)
+        medoid_best = self._buf(max(I, 1), torch.int64)
+        item_inst = self._buf(max(I, 1))
         self._call("scan", "cm3d_scan_segments", _ptr(tile_cnt), _ptr(tile_inst_cnt), _ptr(db.tab("frame_desc")), F,
                pb.max_inst_per_frame, I, _ptr(inst_desc), seg_cap, _ptr(tile_prefix), _ptr(o("frame_n")),
                _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(o("item_off")), _ptr(item_inst),
                _ptr(medoid_best), _ptr(o("errflags")), st)
         self.launches += 2
-        seg_point_idx = torch.empty(seg_cap, **i32)
-        seg_xyzw = torch.empty(4 * seg_cap, dtype=torch.float32, device=dev)
+        seg_point_idx = self._buf(seg_cap)
+        seg_xyzw = self._buf(4 * seg_cap, torch.float32)
         self._call("compact", "cm3d_compact_segments", _ptr(xyzw), _ptr(tile_cnt), _ptr(tile_prefix), _ptr(db.tab("tile_sweep")),
                T, _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
                _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
@@ -343,16 +359,16 @@ class Lifter:
         seg_off_raw = None
         if denoise is not None and I:
             radius, min_nb = float(denoise[0]), int(denoise[1])
-            keep = torch.empty(seg_cap, dtype=torch.uint8, device=dev)
-            item_first = torch.empty(I + 1, **i32)
+            keep = self._buf(seg_cap, torch.uint8)
+            item_first = self._buf(I + 1)
             seg_off2 = torch.zeros(I + 2, **i32)
             kept = ctypes.c_void_p(seg_off2.data_ptr() + 4)          # counts staged at seg_off2[1..]
             self._call("denoise", "cm3d_neighbor_filter", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I,
                        seg_cap // MEDOID_COLS + I, radius, min_nb, _ptr(item_first), _ptr(keep), kept, st)
             self._call("denoise", "cm3d_schedule_segments", _ptr(db.tab("frame_desc")), _ptr(inst_desc), I, seg_cap,
                        _ptr(seg_off2), _ptr(o("item_off")), _ptr(item_inst), _ptr(medoid_best), _ptr(o("errflags")), st)
-            seg_point_idx2 = torch.empty(seg_cap, **i32)
-            seg_xyzw2 = torch.empty(4 * seg_cap, dtype=torch.float32, device=dev)
+            seg_point_idx2 = self._buf(seg_cap)
+            seg_xyzw2 = self._buf(4 * seg_cap, torch.float32)
             self._call("denoise", "cm3d_filter_segments", _ptr(seg_xyzw), _ptr(seg_point_idx), seg_cap, _ptr(o("seg_off")),
                        _ptr(keep), _ptr(seg_off2), I, _ptr(seg_xyzw2), _ptr(seg_point_idx2), _ptr(o("errflags")), st)
             self.launches += 4
@@ -381,10 +397,10 @@ class Lifter:
         if want_obb is None:
             want_obb = pb.any_kitti
         if want_obb and I:
-            obb = torch.empty(I * 16, dtype=torch.float32, device=dev)
-            hull_info = torch.empty(I, **i32)
+            obb = self._buf(I * 16, torch.float32)
+            hull_info = self._buf(I)
             ws_words = int(N.load().cm3d_hull_obb_ws_words(seg_cap)) if self.obb_mode == 0 else 1
-            hull_ws = torch.empty(ws_words, **i32)
+            hull_ws = self._buf(ws_words)
             self._call("hull_obb", "cm3d_hull_obb", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, 4, int(self.obb_mode),
                        _ptr(item_inst), _ptr(hull_ws), ws_words, _ptr(obb), _ptr(hull_info), _ptr(o("errflags")), st)
             self.launches += 1
@@ -416,16 +432,16 @@ class Lifter:
             return out[a:a + max(n, 1)]
 
         # ---- medoid (screen + verify for instances of >= screen_min_pts points, see csrc/medoid.cu)
-        col_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if want_col_sums else None
+        col_sums = self._buf(seg_cap, torch.float32) if want_col_sums else None
         screen_stats = screen_min = None
         if do_medoid and I:
             max_items = seg_cap // MEDOID_COLS + 2 * I
             screen = self.screen_min_pts > 0 and not want_col_sums
-            screen_sums = torch.empty(seg_cap, dtype=torch.float32, device=dev) if screen else None
-            screen_min = torch.empty(5 * I, **i32) if screen else None
-            sym_ws = torch.empty(5 * seg_cap, dtype=torch.float32, device=dev) if screen and not (self.screen_flags & 3) else None
+            screen_sums = self._buf(seg_cap, torch.float32) if screen else None
+            screen_min = self._buf(5 * I) if screen else None
+            sym_ws = self._buf(5 * seg_cap, torch.float32) if screen and not (self.screen_flags & 3) else None
             screen_stats = torch.zeros(1, **i32) if screen else None
-            item_pos = torch.empty(4 * max_items, **i32)     # item_info: {instance, q, o, m} per item
+            item_pos = self._buf(4 * max_items)     # item_info: {instance, q, o, m} per item
             self._call("medoid", "cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), _ptr(seg_point_idx),
                    _ptr(o("item_off")), _ptr(item_inst), I, max_items, _ptr(medoid_best), _ptr(col_sums),
                    _ptr(screen_sums), _ptr(screen_min), int(self.screen_min_pts) if screen else 0, int(self.screen_flags), _ptr(sym_ws),
@@ -441,7 +457,7 @@ class Lifter:
             if len(kitti_flags) > 1:
                 raise ValueError("box_search: a batch must not mix KITTI (y up) with nuScenes/Waymo (z up) frames")
             up_axis = 1 if pb.any_kitti else 2
-            box = torch.empty(I * 8, dtype=torch.float32, device=dev)
+            box = self._buf(I * 8, torch.float32)
             self._call("box_search", "cm3d_box_search", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, up_axis,
                        int(box_search), 1, _ptr(box), _ptr(o("errflags")), st)
             self.launches += 1
@@ -473,7 +489,7 @@ class Lifter:
         return res
 
     @_on_device
-    def lift_frame_stream(self, frames, batch_frames: int = 32, timer: Optional[dict] = None, depth: int = 2,
+    def lift_frame_stream(self, frames, batch_frames: int = 32, timer: Optional[dict] = None, depth: int = 3,
                           pack_workers: int = 4):
         """Drop-in scripts' entry: an iterator of FrameSpecs in, lists of LiftResult (one list per
         batch of `batch_frames` frames, frame order kept) out.  Batches are packed into pinned
@@ -542,7 +558,7 @@ class Lifter:
             sys.setswitchinterval(old_interval)
 
     @_on_device
-    def lift_packed_stream(self, batches, seg_cap: Optional[int] = None, depth: int = 2, with_handles: bool = False):
+    def lift_packed_stream(self, batches, seg_cap: Optional[int] = None, depth: int = 3, with_handles: bool = False):
         """Pipelined bulk path (config C5: tens of thousands of frames): yields the label dict of
         every PackedBatch in order.  Batch k+1 is copied host->device on a copy stream while batch
         k runs on the compute stream; the small result block comes back asynchronously into

@@ -48,14 +48,14 @@ def launches(path, tag, cmd):
     tot = sum(a[1] for a in agg.values())
     out = os.path.join(ROOT, "profiles", f"{tag}_ncu_launch_summary.csv")
     with open(out, "w") as f:
-        f.write(f"# {tag} ncu launch list summary (`{cmd}`, 64 C2 frames/step, B200)\n")
+        f.write(f"# {tag} ncu launch list summary (`{cmd}`, B200)\n")
         f.write("# per-launch times are cold-cache and serialised under ncu: compare SHARES, not absolutes; "
                 "dram_MB = dram__bytes_read+write per launch\n")
         f.write("kernel,launches,avg_us,share,dram_MB_per_launch\n")
         for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{k},{a[0]},{a[1] / a[0] / 1e3:.1f},{a[1] / tot:.4f},{a[2] / a[0] / 1e6:.1f}\n")
     tj = {"source": f"profiles/{tag}_ncu_launch_summary.csv (ncu launch list of `{cmd}`, batch 64 C2 frames)",
-          "frames_per_launch": 64,
+          "frames_per_launch": 64, "config": "c2",
           "dram_bytes_per_launch": {k.replace("cm3d::", ""): int(a[2] / a[0]) for k, a in agg.items() if k.startswith("cm3d::")}}
     with open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w") as f:
         json.dump(tj, f, indent=1)
