@@ -545,10 +545,13 @@ def run_ours(args, rank, world, local_rank):
                     return 256.0 * 256.0 * fb * (fb + 1) / 2.0 + (x - 256.0 * fb) * x
                 g2 = np.maximum(mm - g0 - g1, 0.0)
                 grouped = tri(g0) + tri(g2) + (mm * mm - g0 * g0 - g2 * g2)      # both groups symmetric, the rest in both orders
-                roots = float(np.where(modes == 2, tri(mm), np.where(modes == 3, grouped, mm * mm)).sum())
+                roots = float(np.where(modes == 2, tri(mm), np.where(modes == 3, grouped, np.where(modes == 4, g0 * mm, mm * mm))).sum())
                 kern["medoid"]["instances_by_mode"] = {"exact": int((modes == 0).sum()), "screen_all_pairs": int((modes == 1).sum()),
                                                        "screen_symmetric": int((modes == 2).sum()),
-                                                       "screen_grouped_symmetric": int((modes == 3).sum())}
+                                                       "screen_grouped_symmetric": int((modes == 3).sum()),
+                                                       "screen_pruned_columns": int((modes == 4).sum())}
+                if (modes == 4).any():
+                    kern["medoid"]["pruned_columns_kept"] = float(g0[modes == 4].sum() / mm[modes == 4].sum())
             roots *= prs / max(pairs[0], 1.0)        # batch 0's root count scaled to the mean batch
             kern["medoid"]["bound"] = ("XU pipe: one MUFU.SQRT per evaluated pair distance in the screen pass (reads only "
                                        "sum M points, L2-resident); symmetric instances evaluate the pairs i <= j only")

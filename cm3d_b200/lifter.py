@@ -193,10 +193,12 @@ class Lifter:
         self.stream_stats = {}      # seconds the streaming path spent waiting for packers / the GPU / enqueueing (diagnostics)
         self.screen_min_pts = SCREEN_MIN_PTS   # medoid: instances this large are screened, then verified; 0 = all exact
         self.screen_flags = 0                  # bit 0: no symmetric screen (every screened instance does all M^2 pairs);
-        #                                        bit 1: no grouped symmetric screen for instances that straddle two binades
+        #                                        bit 1: no grouped symmetric screen for instances that straddle two binades;
+        #                                        bit 2: no exact column pruning for sensor-frame clouds
         self.last_screen_stats = None          # device int32[1]: columns the last run() verified exactly
-        self.last_screen_modes = None          # device int32[3 I]: mode (0 exact, 1 all pairs, 2 symmetric, 3 grouped
-        #                                        symmetric) | points in group 0 | points in the sliver group (mode 3)
+        self.last_screen_modes = None          # device int32[3 I]: mode (0 exact, 1 all pairs, 2 symmetric, 3 grouped symmetric,
+        #                                        4 all pairs over pruned columns) | points in group 0 (mode 3) or columns kept
+        #                                        (mode 4) | points in the sliver group (mode 3)
         self.timing = None          # dict label -> [(start_event, end_event)] when bench.py profiles
         self.obb_mode = 0           # KITTI box: 0 = hull vertices (open3d's algorithm), 1 = all member points (diagnostics)
         self.last_hull_info = None  # device int32[I]: hull vertex count per instance (-1: flat cloud -> the reference's fallback box)

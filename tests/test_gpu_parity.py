@@ -314,16 +314,16 @@ def test_medoid_screen_equals_exact(lifter):
             if c.shape[1] < thr:
                 assert modes[k] == 0
             elif flags & 1:
-                assert modes[k] in (0, 1)
+                assert modes[k] in (0, 1, 4)        # 4 = all pairs over the columns k_medoid_prune left
             elif flags & 2:
-                assert modes[k] in (0, 1, 2)
+                assert modes[k] in (0, 1, 2, 4)
         if flags == 0:
             # global-frame clouds around (1200, 950, 1) sit inside one binade of |p|^2: symmetric screen;
             # the ones centred on (1024, 1024, 0) straddle 2^21: all-pairs screen
             g = [k for k, c in enumerate(cases) if c.shape[1] >= 512 and abs(c[0].mean() - 1200) < 1 and abs(c[1].mean() - 950) < 1]
             assert len(g) >= 20 and all(modes[k] == 2 for k in g)
             st = [k for k, c in enumerate(cases) if c.shape[1] >= 700 and c[0].std() > 1.0 and abs(c[0].mean() - 1024) < 0.5 and abs(c[1].mean() - 1024) < 0.5]
-            assert len(st) == 2 and all(modes[k] in (1, 3) for k in st)
+            assert len(st) == 2 and all(modes[k] in (1, 3, 4) for k in st)
             assert (modes == 2).sum() >= 30
             tw = [k for k, c in enumerate(cases) if c.shape[1] in (2400, 2403, 700) and abs(c[0].mean() - 1022.3) < 0.5 and c[0].std() > 2.0]
             assert len(tw) == 3 and all(modes[k] == 3 for k in tw), (tw, [modes[k] for k in tw])
@@ -870,3 +870,36 @@ def test_medoid_is_a_true_near_minimum(lifter):
     assert checked >= 60
     for ds in ("kitti", "waymo"):
         assert agree[ds][0] >= 0.9 * agree[ds][1], (ds, agree)
+
+
+def test_medoid_column_pruning_equals_exact(lifter):
+    """Sensor-frame clouds (KITTI / Waymo magnitudes): k_medoid_prune drops columns by pivot bounds before the
+    all-pairs screen; the medoid must stay the all-exact kernel's on surfaces, blobs, duplicates, clouds whose
+    medoid sits at the edge of the index range, and clouds where nothing can be pruned."""
+    rng = np.random.default_rng(11)
+    cases = []
+    def box_surface(m, centre, ext, yaw):
+        f = rng.integers(0, 3, m)
+        u, v = rng.uniform(-0.5, 0.5, m), rng.uniform(-0.5, 0.5, m)
+        p = np.stack([np.where(f == 0, 0.5, u), np.where(f == 1, -0.5, np.where(f == 0, v, u * 0 + v)), np.where(f == 2, 0.5, v)], 1) * ext
+        c, s = np.cos(yaw), np.sin(yaw)
+        p = p @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]]).T + centre
+        return (p + rng.normal(0, 0.01, p.shape)).T.astype(np.float32)
+    for m in (1024, 1500, 2049, 4000, 7777, 12000):
+        cases.append(box_surface(m, np.array([rng.uniform(-20, 20), 1.0, rng.uniform(8, 50)]), np.array([4.5, 1.5, 1.8]), rng.uniform(0, 3)))
+    for m in (1100, 3000):
+        cases.append((rng.normal(0, 1.0, (3, m)) + np.array([[5.0], [-1.0], [25.0]])).astype(np.float32))            # blob
+        cases.append((rng.normal(0, 0.05, (3, m)) + np.array([[0.5], [0.2], [3.0]])).astype(np.float32))             # tiny object: slack dominates
+    d = box_surface(2500, np.array([3.0, 1.0, 15.0]), np.array([4.0, 1.6, 1.5]), 0.4)
+    cases.append(np.concatenate([d, d[:, :700]], 1))                                                                  # duplicates
+    far = (rng.normal(0, 6, (3, 2000)) + np.array([[0.0], [0.0], [40.0]])).astype(np.float32)
+    clump = (rng.normal(0, 0.02, (3, 300)) + np.array([[0.0], [0.0], [40.0]])).astype(np.float32)
+    cases.append(np.concatenate([clump, far], 1))                                                                      # medoid among the first columns
+    cases.append(np.concatenate([far, clump], 1))                                                                      # ... among the last (tail) columns
+    exact, _, _ = _medoid_abi(cases, 0)
+    got, _, _ = _medoid_abi(cases, 512)
+    modes = _medoid_abi.last_modes.copy()
+    nop, _, _ = _medoid_abi(cases, 512, screen_flags=4)
+    assert np.array_equal(got, exact) and np.array_equal(nop, exact)
+    assert (modes == 4).sum() >= 3, modes                       # some of these really were pruned (others are symmetric-eligible)
+    assert (_medoid_abi.last_modes == 4).sum() == 0             # and the flag switches it off
