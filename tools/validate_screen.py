@@ -18,11 +18,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     cfg = sys.argv[3] if len(sys.argv) > 3 else "c2"
-    if cfg == "c2":
-        frames = bench.make_frames(first, n, 16)
-    else:
-        from cm3d_b200 import synthetic as S
-        frames = [S.make_frame(cfg, first + i) for i in range(n)]
+    frames = bench.make_frames({"c2": "c5"}.get(cfg, cfg), first, n, 16)
     lifter = Lifter("cuda:0")
     pb = lifter.pack(frames)
     db = lifter.upload(pb)
@@ -38,6 +34,8 @@ def main():
     m = out[0][3]
     for thr in (512, 32):
         bad = np.flatnonzero(out[thr][0] != out[0][0])
+        modes = lifter.last_screen_modes.cpu().numpy()[:m.size]
+        print(f"modes (0 exact, 1 all pairs, 2 symmetric, 3 grouped, 4 pruned): {np.bincount(modes, minlength=5).tolist()}", flush=True)
         print(f"{cfg} frames {first}..{first + n - 1} screen_min_pts={thr}: {m.size} instances, {int((m >= max(thr, 32)).sum())} screened, "
               f"{out[thr][2]} columns verified, {bad.size} disagreements {bad[:10].tolist()}", flush=True)
         assert bad.size == 0 and np.array_equal(out[thr][1], out[0][1])
