@@ -341,18 +341,23 @@ def run_ours(args, rank, world, local_rank):
     # the front end (masks, aggregation, projection, gather: HBM-bound) is launched on a high-priority stream and
     # the medoid (XU-bound) on the lifter's second stream, so step k+1's front end runs next to step k's medoid
     front = torch.cuda.Stream(dev, priority=-1) if overlap else cur
-    for w in range(3):
+    import collections
+    # the last eight steps' buffers stay referenced (as in the streaming path's pipeline): a workspace that is
+    # freed while the other stream still uses it cannot be reused, and the allocator would cudaMalloc a new one
+    ring = collections.deque(maxlen=8 if overlap else 1)
+    for w in range(9):
         with torch.cuda.stream(front):
-            do = lifter.run(dbs[w % n_res], seg_cap=seg_cap, overlap=overlap)
-        del do
+            ring.append(lifter.run(dbs[w % n_res], seg_cap=seg_cap, overlap=overlap))
     barrier()
     e0.record(cur)
     front.wait_stream(cur)
-    do = None
     with torch.cuda.stream(front):
         for k in range(args.steps):
-            del do                          # free the previous step's buffers first: no third workspace, no cudaMalloc
-            do = lifter.run(dbs[k % n_res], seg_cap=seg_cap, overlap=overlap)
+            if overlap and len(ring) == ring.maxlen:
+                ring[0].done.synchronize()      # the host stays at most eight steps ahead (the GPU always has work queued):
+                #                                 buffers are then freed AFTER their last use and recycled without cudaMalloc
+            ring.append(lifter.run(dbs[k % n_res], seg_cap=seg_cap, overlap=overlap))
+    do = ring[-1]
     if overlap:
         cur.wait_event(do.done)             # the medoid stream is in order: the last step's event covers every step
     cur.wait_stream(front)
@@ -365,6 +370,7 @@ def run_ours(args, rank, world, local_rank):
     last = (args.steps - 1) % n_res
     assert np.array_equal(final["medoid_point_idx"], first_labels[last]["medoid_point_idx"])       # deterministic labels
     del do
+    ring.clear()
 
     # ---- per-kernel CUDA events: a separate pass over every resident batch (not inside the headline region)
     lifter.timing = {}

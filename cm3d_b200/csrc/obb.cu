@@ -93,14 +93,29 @@ __device__ void jacobi3(double a[3][3], double v[3][3])
 }
 
 // ------------------------------------------------------------------------------------------ hull vertices
+// fp64 copies of the wrapped points in shared memory were tried (no float -> double conversion inside the tournaments):
+// they cost a quarter of the survivor capacity and ran 2.4x slower on C3 (6.2 ms against 2.6 ms per 32 frames)
+#ifndef CM3D_HULL_DOUBLE
+#define CM3D_HULL_DOUBLE 0
+#endif
+#ifndef CM3D_HULL_CACHED
+#define CM3D_HULL_CACHED 1
+#endif
+#if CM3D_HULL_DOUBLE
+typedef double hull_coord_t;
+#else
+typedef float hull_coord_t;
+#endif
 constexpr int kHullThreads = 512;
 
 struct HullPts {
-    const float *x, *y, *z;
+    const float *x, *y, *z;            // fp32 coordinates in global memory, or ...
+    const hull_coord_t *dx, *dy, *dz;  // ... copies in shared memory (dx != nullptr; fp64: no conversion inside the tournaments)
     int m;
     __device__ __forceinline__ void get(int r, double &px, double &py, double &pz) const
     {
-        px = (double)x[r]; py = (double)y[r]; pz = (double)z[r];      // global or shared memory
+        if (dx) { px = (double)dx[r]; py = (double)dy[r]; pz = (double)dz[r]; }
+        else { px = (double)x[r]; py = (double)y[r]; pz = (double)z[r]; }
     }
 };
 
@@ -421,17 +436,30 @@ __device__ void face_commit(WrapTables &W, int s, int t, int p, uint8_t *vflag, 
 __device__ int hull_wrap_warp(const HullPts &P, const HullEdge &E, int s, int t)
 {
     const int lane = (int)lane_id();
+    // thread-local pass with the normal of the current best plane cached: one difference and one dot product per
+    // point; the full comparison (tie rules, lower index first) only when the dot product is exactly zero
     int best = -1;
+    double nx = 0.0, ny = 0.0, nz = 0.0;
     for (int r = lane; r < P.m; r += 32) {
         if (r == s || r == t) continue;
+        double wx, wy, wz;
+        P.get(r, wx, wy, wz);
+        wx -= E.sx; wy -= E.sy; wz -= E.sz;
+        bool take;
         if (best < 0) {
-            double wx, wy, wz;
-            P.get(r, wx, wy, wz);
-            wx -= E.sx; wy -= E.sy; wz -= E.sz;
-            const double nx = E.ey * wz - E.ez * wy, ny = E.ez * wx - E.ex * wz, nz = E.ex * wy - E.ey * wx;
-            if (nx * nx + ny * ny + nz * nz > 0.0) best = r;
-        } else if (hull_beats(P, E, best, r)) {
-            best = r;
+            take = true;
+        } else {
+#if CM3D_HULL_CACHED
+            const double d = nx * wx + ny * wy + nz * wz;         // > 0: r lies outside the plane (S, T, best)
+            take = d > 0.0 || (d == 0.0 && hull_beats(P, E, best, r));
+#else
+            take = hull_beats(P, E, best, r);
+#endif
+        }
+        if (take) {
+            const double cx = E.ey * wz - E.ez * wy, cy = E.ez * wx - E.ex * wz, cz = E.ex * wy - E.ey * wx;
+            if (best < 0 && !(cx * cx + cy * cy + cz * cz > 0.0)) continue;      // on the edge's line: never a third vertex
+            best = r; nx = cx; ny = cy; nz = cz;
         }
     }
 #pragma unroll
@@ -520,15 +548,17 @@ __device__ int hull_vertices_par(const HullPts &P, WrapTables &W, int32_t *faces
 // whose coarse hull is flat, whose coarse face count is inconsistent, or whose survivors do not fit falls
 // back to wrapping every point from global memory.
 constexpr int kHullDirs = 256;
-constexpr int kHullSurvCap = 4096;
+constexpr int kHullSurvCap = CM3D_HULL_DOUBLE ? 3072 : 4096;
 constexpr int kHullDirect = 768;             // clouds this small are wrapped directly (in shared memory)
 constexpr int kCoarseFaceCap = 2 * kHullDirs;
 
 struct HullShared {
-    float sx[kHullSurvCap], sy[kHullSurvCap], sz[kHullSurvCap];
+    hull_coord_t sx[kHullSurvCap], sy[kHullSurvCap], sz[kHullSurvCap];
     int32_t sorig[kHullSurvCap];
     uint8_t sflag[kHullSurvCap];
     double plane[kCoarseFaceCap][4];
+    float4 plane32[kCoarseFaceCap];          // the same planes in fp32 (offset without the guard band) ...
+    float margin32[kCoarseFaceCap];          // ... and the band inside which the fp32 value decides nothing
     int32_t cfaces[3 * kCoarseFaceCap];
     float dirs[kHullDirs][3];
     int32_t ext[kHullDirs];
@@ -615,21 +645,25 @@ __device__ int hull_vertices_filtered(HullShared &S, const float *sx, const floa
         int n_dir = min(kHullDirs, max(32, m / 32)) & ~7;
         hull_extremes(S, sx, sy, sz, m, n_dir);
         // distinct extreme points, in direction order -> the coarse set in S.sx/sy/sz[0..nc)
-        if (threadIdx.x == 0) S.count = 0;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int nc = 0;
-            for (int k = 0; k < n_dir; ++k) {
-                const int e = S.ext[k];
-                bool dup = e < 0;
-                for (int j = 0; j < nc && !dup; ++j) dup = S.sorig[j] == e;
-                if (!dup) { S.sorig[nc] = e; S.sx[nc] = sx[e]; S.sy[nc] = sy[e]; S.sz[nc] = sz[e]; ++nc; }
+        {   // thread k owns direction k: unique when no earlier direction found the same point; ranks by ballot
+            const int k = threadIdx.x;
+            const int e = k < n_dir ? S.ext[k] : -1;
+            bool uniq = e >= 0;
+            for (int j = 0; j < k && uniq; ++j) uniq = S.ext[j] != e;
+            const unsigned bal = __ballot_sync(0xffffffffu, uniq);
+            if (lane_id() == 0) S.wsum[threadIdx.x >> 5] = __popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { if (w < (int)(threadIdx.x >> 5)) before += S.wsum[w]; total += S.wsum[w]; }
+            if (uniq) {
+                const int at = before + __popc(bal & lanemask_lt());
+                S.sorig[at] = e; S.sx[at] = sx[e]; S.sy[at] = sy[e]; S.sz[at] = sz[e];
             }
-            S.count = nc;
+            if (threadIdx.x == 0) S.count = total;
+            __syncthreads();
         }
-        __syncthreads();
         const int nc = S.count;
-        HullPts C{S.sx, S.sy, S.sz, nc};
+        HullPts C{nullptr, nullptr, nullptr, S.sx, S.sy, S.sz, nc};
         const int nf = nc >= 4 ? hull_vertices_par(C, S.W, S.cfaces, kCoarseFaceCap, S.sflag, s_cand) : 0;
         __syncthreads();
         bool usable = nf >= 4;
@@ -646,6 +680,16 @@ __device__ int hull_vertices_filtered(HullShared &S, const float *sx, const floa
             __syncthreads();
         }
         if (usable) {
+            // |p|_1 of the farthest point: the scale of every plane evaluation's rounding error
+            float r1 = 0.0f;
+            for (int r = threadIdx.x; r < m; r += blockDim.x) r1 = fmaxf(r1, fabsf(sx[r]) + fabsf(sy[r]) + fabsf(sz[r]));
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) r1 = fmaxf(r1, __shfl_xor_sync(0xffffffffu, r1, o2));
+            if (lane_id() == 0) S.wsum[threadIdx.x >> 5] = __float_as_int(r1);
+            __syncthreads();
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r1 = fmaxf(r1, __int_as_float(S.wsum[w]));
+            const double Rcloud = (double)r1 * 1.000001;
+            __syncthreads();
             for (int f = threadIdx.x; f < nf; f += blockDim.x) {
                 const int a = S.cfaces[3 * f], b = S.cfaces[3 * f + 1], c = S.cfaces[3 * f + 2];
                 const double ax = S.sx[a], ay = S.sy[a], az = S.sz[a];
@@ -654,9 +698,12 @@ __device__ int hull_vertices_filtered(HullShared &S, const float *sx, const floa
                 const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;     // outward
                 const double off = -(nx * ax + ny * ay + nz * az);
                 // guard band: |rounding of n.p + off| <= ~8 ulp of |n|_1 * max|coordinate|; 2^-40 is 10^3 times that
-                const double R = fabs(ax) + fabs(ay) + fabs(az) + fabs(ux) + fabs(uy) + fabs(uz) + fabs(vx) + fabs(vy) + fabs(vz);
+                const double R = Rcloud + fabs(ax) + fabs(ay) + fabs(az);      // |n.p| + |off| <= |n|_1 R
                 S.plane[f][0] = nx; S.plane[f][1] = ny; S.plane[f][2] = nz;
                 S.plane[f][3] = off + (fabs(nx) + fabs(ny) + fabs(nz)) * R * 0x1p-40;                   // inside iff n.p + this < 0
+                // fp32 screen of the same test: rounding the four constants and three FMAs is below 2^-21 |n|_1 R
+                S.plane32[f] = make_float4((float)nx, (float)ny, (float)nz, (float)off);
+                S.margin32[f] = (float)((fabs(nx) + fabs(ny) + fabs(nz)) * R * 0x1p-19);
             }
             __syncthreads();
             // survivors, in index order (ballot ranks + a scan of the warp totals per chunk of blockDim points)
@@ -670,8 +717,14 @@ __device__ int hull_vertices_filtered(HullShared &S, const float *sx, const floa
                 if (r < m) {
                     x = sx[r]; y = sy[r]; z = sz[r];
                     const double px = x, py = y, pz = z;
-                    for (int f = 0; f < nf; ++f)
-                        if (!(S.plane[f][0] * px + S.plane[f][1] * py + S.plane[f][2] * pz + S.plane[f][3] < 0.0)) { keep = true; break; }
+                    for (int f = 0; f < nf; ++f) {
+                        const float4 pl = S.plane32[f];
+                        const float v = fmaf(pl.x, x, fmaf(pl.y, y, fmaf(pl.z, z, pl.w)));
+                        const float mg = S.margin32[f];
+                        if (v < -mg) continue;                              // clearly inside this face
+                        if (v > mg ||                                       // clearly outside; in between fp64 decides
+                            !(S.plane[f][0] * px + S.plane[f][1] * py + S.plane[f][2] * pz + S.plane[f][3] < 0.0)) { keep = true; break; }
+                    }
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, keep);
                 if (lane == 0) S.wsum[warp] = __popc(bal);
@@ -697,10 +750,10 @@ __device__ int hull_vertices_filtered(HullShared &S, const float *sx, const floa
     }
     __syncthreads();
     if (ns < 0) {                                 // fallback: every point, from global memory
-        HullPts P{sx, sy, sz, m};
+        HullPts P{sx, sy, sz, nullptr, nullptr, nullptr, m};
         return hull_vertices(P, faces_ws, 2 * m, vflag, s_cand);
     }
-    HullPts P{S.sx, S.sy, S.sz, ns};
+    HullPts P{nullptr, nullptr, nullptr, S.sx, S.sy, S.sz, ns};
     int n_faces = hull_vertices_par(P, S.W, nullptr, 0, S.sflag, s_cand);
     __syncthreads();
     if (n_faces < 0) n_faces = hull_vertices(P, faces_ws, 2 * m, S.sflag, s_cand);       // tables overflowed: one edge at a time

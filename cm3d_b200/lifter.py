@@ -21,8 +21,11 @@ from .batch import (ERR_WORDS, FR_WORDS, MAX_INST, MEDOID_COLS, SCREEN_MIN_PTS, 
 from .frames import FrameSpec, LiftResult
 
 
-def _ptr(t: Optional[torch.Tensor]):
-    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+def _ptr(t):
+    """Device pointer of a tensor (or an address already taken, or None) as a ctypes argument."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t if isinstance(t, int) else t.data_ptr())
 
 
 @dataclass
@@ -36,6 +39,10 @@ class DeviceBatch:
     def tab(self, name: str) -> torch.Tensor:
         o = self.pb.off[name]
         return self.meta[o:o + self.pb.off[name + "_n"]]
+
+    def tab_ptr(self, name: str) -> int:
+        """Address of a descriptor table (no tensor view: the launch sequence asks for ~30 of these per batch)."""
+        return self.meta.data_ptr() + 4 * self.pb.off[name]
 
 
 @dataclass
@@ -288,11 +295,16 @@ class Lifter:
             a, n = lay[name]
             return out[a:a + max(n, 1)]
 
+        out_base = out.data_ptr()
+
+        def op(name):                       # address of a field of the label block
+            return out_base + 4 * lay[name][0]
+
         # ---- masks -> eroded bit planes (+ bbox)
         bits_raw = self._buf(max(pb.bits_words, 1))
         bits = self._buf(max(pb.bits_words, 1))
         bbox = self._buf(max(I, 1) * 4)
-        inst_desc = db.tab("inst_desc")
+        inst_desc = db.tab_ptr("inst_desc")
         row_range = None
         if I:
             if pb.masks_kind == "dense":
@@ -309,7 +321,7 @@ class Lifter:
                 run_start = self._buf(max(runs.numel(), 1))
                 row_range = self._buf(2 * I)
                 self._call("masks_rle", "cm3d_masks_fill_rle", _ptr(runs), _ptr(db.mask_off), _ptr(run_start), _ptr(inst_desc),
-                       I, pb.max_runs, _ptr(bits_raw), _ptr(row_range), _ptr(o("errflags")), st)
+                       I, pb.max_runs, _ptr(bits_raw), _ptr(row_range), _ptr(op("errflags")), st)
                 self.launches += 2              # k_rle_prefix, k_rle_fill (torch's zero fill of the planes is not ours)
             self._call("masks_erode", "cm3d_masks_erode3x3", _ptr(bits_raw), _ptr(inst_desc), _ptr(row_range), I,
                        pb.max_words, _ptr(bits), _ptr(bbox), st)
@@ -317,16 +329,16 @@ class Lifter:
 
         vcam_grid = self._buf(max(pb.grid_words, 1))
         if I:
-            self._call("vcam_grid", "cm3d_build_vcam_grid", _ptr(db.tab("vcam_desc")), pb.n_vcams, pb.max_cells,
-                       _ptr(db.tab("frame_desc")), _ptr(db.tab("cam_inst_list")), _ptr(bbox), _ptr(vcam_grid), st)
+            self._call("vcam_grid", "cm3d_build_vcam_grid", _ptr(db.tab_ptr("vcam_desc")), pb.n_vcams, pb.max_cells,
+                       _ptr(db.tab_ptr("frame_desc")), _ptr(db.tab_ptr("cam_inst_list")), _ptr(bbox), _ptr(vcam_grid), st)
             self.launches += 1
 
         # ---- sweeps -> aggregated cloud
         xyzw = self._buf(4 * n_slots, torch.float32)
         tile_cnt = self._buf(max(T, 1))
         tile_prefix = self._buf(max(T, 1))
-        self._call("aggregate", "cm3d_aggregate_sweeps", _ptr(db.raw), _ptr(db.tab("tile_sweep")), T, _ptr(db.tab("sweep_desc")),
-               _ptr(db.tab("frame_desc")), _ptr(db.tab("chains")), _ptr(xyzw), _ptr(tile_cnt), st)
+        self._call("aggregate", "cm3d_aggregate_sweeps", _ptr(db.raw), _ptr(db.tab_ptr("tile_sweep")), T, _ptr(db.tab_ptr("sweep_desc")),
+               _ptr(db.tab_ptr("frame_desc")), _ptr(db.tab_ptr("chains")), _ptr(xyzw), _ptr(tile_cnt), st)
         self.launches += 1 if T else 0
 
         # ---- projection + membership (count pass)
@@ -334,27 +346,27 @@ class Lifter:
         tile_inst_cnt = self._buf(max(pb.cnt_total, 1), torch.int16)
         tile_inst_base = self._buf(max(pb.cnt_total, 1))
         pix = self._buf(16 * n_slots) if want_pix else None
-        self._call("project_count", "cm3d_project_membership", _ptr(xyzw), _ptr(tile_cnt), _ptr(db.tab("tile_sweep")), T,
-               _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
-               _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
+        self._call("project_count", "cm3d_project_membership", _ptr(xyzw), _ptr(tile_cnt), _ptr(db.tab_ptr("tile_sweep")), T,
+               _ptr(db.tab_ptr("sweep_desc")), _ptr(db.tab_ptr("frame_desc")), _ptr(db.tab_ptr("vcam_desc")),
+               _ptr(db.tab_ptr("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab_ptr("chains")), _ptr(bits),
                _ptr(vcam_grid), _ptr(hits), _ptr(tile_inst_cnt), _ptr(pix), st)
         self.launches += 1 if T else 0
 
         # ---- scans, ordered compaction + gather
         medoid_best = self._buf(max(I, 1), torch.int64)
         item_inst = self._buf(max(I, 1))
-        self._call("scan", "cm3d_scan_segments", _ptr(tile_cnt), _ptr(tile_inst_cnt), _ptr(db.tab("frame_desc")), F,
-               pb.max_inst_per_frame, I, _ptr(inst_desc), seg_cap, _ptr(tile_prefix), _ptr(o("frame_n")),
-               _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(o("item_off")), _ptr(item_inst),
-               _ptr(medoid_best), _ptr(o("errflags")), st)
+        self._call("scan", "cm3d_scan_segments", _ptr(tile_cnt), _ptr(tile_inst_cnt), _ptr(db.tab_ptr("frame_desc")), F,
+               pb.max_inst_per_frame, I, _ptr(inst_desc), seg_cap, _ptr(tile_prefix), _ptr(op("frame_n")),
+               _ptr(tile_inst_base), _ptr(op("seg_off")), _ptr(op("item_off")), _ptr(item_inst),
+               _ptr(medoid_best), _ptr(op("errflags")), st)
         self.launches += 2
         seg_point_idx = self._buf(seg_cap)
         seg_xyzw = self._buf(4 * seg_cap, torch.float32)
-        self._call("compact", "cm3d_compact_segments", _ptr(xyzw), _ptr(tile_cnt), _ptr(tile_prefix), _ptr(db.tab("tile_sweep")),
-               T, _ptr(db.tab("sweep_desc")), _ptr(db.tab("frame_desc")), _ptr(db.tab("vcam_desc")),
-               _ptr(db.tab("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab("chains")), _ptr(bits),
-               _ptr(vcam_grid), _ptr(hits), _ptr(tile_inst_base), _ptr(o("seg_off")), _ptr(seg_point_idx), _ptr(seg_xyzw),
-               seg_cap, pb.max_inst_per_frame, _ptr(o("errflags")), st)
+        self._call("compact", "cm3d_compact_segments", _ptr(xyzw), _ptr(tile_cnt), _ptr(tile_prefix), _ptr(db.tab_ptr("tile_sweep")),
+               T, _ptr(db.tab_ptr("sweep_desc")), _ptr(db.tab_ptr("frame_desc")), _ptr(db.tab_ptr("vcam_desc")),
+               _ptr(db.tab_ptr("cam_inst_list")), _ptr(inst_desc), _ptr(bbox), _ptr(db.tab_ptr("chains")), _ptr(bits),
+               _ptr(vcam_grid), _ptr(hits), _ptr(tile_inst_base), _ptr(op("seg_off")), _ptr(seg_point_idx), _ptr(seg_xyzw),
+               seg_cap, pb.max_inst_per_frame, _ptr(op("errflags")), st)
         self.launches += 1 if T else 0
 
         # ---- default-off: neighbour-count outlier filter -> filtered segments
@@ -365,14 +377,14 @@ class Lifter:
             item_first = self._buf(I + 1)
             seg_off2 = torch.zeros(I + 2, **i32)
             kept = ctypes.c_void_p(seg_off2.data_ptr() + 4)          # counts staged at seg_off2[1..]
-            self._call("denoise", "cm3d_neighbor_filter", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I,
+            self._call("denoise", "cm3d_neighbor_filter", _ptr(seg_xyzw), seg_cap, _ptr(op("seg_off")), I,
                        seg_cap // MEDOID_COLS + I, radius, min_nb, _ptr(item_first), _ptr(keep), kept, st)
-            self._call("denoise", "cm3d_schedule_segments", _ptr(db.tab("frame_desc")), _ptr(inst_desc), I, seg_cap,
-                       _ptr(seg_off2), _ptr(o("item_off")), _ptr(item_inst), _ptr(medoid_best), _ptr(o("errflags")), st)
+            self._call("denoise", "cm3d_schedule_segments", _ptr(db.tab_ptr("frame_desc")), _ptr(inst_desc), I, seg_cap,
+                       _ptr(seg_off2), _ptr(op("item_off")), _ptr(item_inst), _ptr(medoid_best), _ptr(op("errflags")), st)
             seg_point_idx2 = self._buf(seg_cap)
             seg_xyzw2 = self._buf(4 * seg_cap, torch.float32)
-            self._call("denoise", "cm3d_filter_segments", _ptr(seg_xyzw), _ptr(seg_point_idx), seg_cap, _ptr(o("seg_off")),
-                       _ptr(keep), _ptr(seg_off2), I, _ptr(seg_xyzw2), _ptr(seg_point_idx2), _ptr(o("errflags")), st)
+            self._call("denoise", "cm3d_filter_segments", _ptr(seg_xyzw), _ptr(seg_point_idx), seg_cap, _ptr(op("seg_off")),
+                       _ptr(keep), _ptr(seg_off2), I, _ptr(seg_xyzw2), _ptr(seg_point_idx2), _ptr(op("errflags")), st)
             self.launches += 4
             seg_off_raw = o("seg_off")[:I + 1].clone()
             o("seg_off")[:I + 1].copy_(seg_off2[:I + 1])
@@ -403,8 +415,8 @@ class Lifter:
             hull_info = self._buf(I)
             ws_words = int(N.load().cm3d_hull_obb_ws_words(seg_cap)) if self.obb_mode == 0 else 1
             hull_ws = self._buf(ws_words)
-            self._call("hull_obb", "cm3d_hull_obb", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, 4, int(self.obb_mode),
-                       _ptr(item_inst), _ptr(hull_ws), ws_words, _ptr(obb), _ptr(hull_info), _ptr(o("errflags")), st)
+            self._call("hull_obb", "cm3d_hull_obb", _ptr(seg_xyzw), seg_cap, _ptr(op("seg_off")), I, 4, int(self.obb_mode),
+                       _ptr(item_inst), _ptr(hull_ws), ws_words, _ptr(obb), _ptr(hull_info), _ptr(op("errflags")), st)
             self.launches += 1
             if phase2 is not None:
                 ev_hull = torch.cuda.Event()
@@ -433,6 +445,11 @@ class Lifter:
             a, n = lay[name]
             return out[a:a + max(n, 1)]
 
+        out_base = out.data_ptr()
+
+        def op(name):                       # address of a field of the label block
+            return out_base + 4 * lay[name][0]
+
         # ---- medoid (screen + verify for instances of >= screen_min_pts points, see csrc/medoid.cu)
         col_sums = self._buf(seg_cap, torch.float32) if want_col_sums else None
         screen_stats = screen_min = None
@@ -444,11 +461,11 @@ class Lifter:
             sym_ws = self._buf(5 * seg_cap, torch.float32) if screen and not (self.screen_flags & 3) else None
             screen_stats = torch.zeros(1, **i32) if screen else None
             item_pos = self._buf(4 * max_items)     # item_info: {instance, q, o, m} per item
-            self._call("medoid", "cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), _ptr(seg_point_idx),
-                   _ptr(o("item_off")), _ptr(item_inst), I, max_items, _ptr(medoid_best), _ptr(col_sums),
+            self._call("medoid", "cm3d_medoid", _ptr(seg_xyzw), seg_cap, _ptr(op("seg_off")), _ptr(seg_point_idx),
+                   _ptr(op("item_off")), _ptr(item_inst), I, max_items, _ptr(medoid_best), _ptr(col_sums),
                    _ptr(screen_sums), _ptr(screen_min), int(self.screen_min_pts) if screen else 0, int(self.screen_flags), _ptr(sym_ws),
                    _ptr(screen_stats), _ptr(item_pos),
-                   _ptr(o("medoid_local")), _ptr(o("medoid_point_idx")), _ptr(o("centroid")), _ptr(o("errflags")), st)
+                   _ptr(op("medoid_local")), _ptr(op("medoid_point_idx")), _ptr(op("centroid")), _ptr(op("errflags")), st)
             # expand_items, k_medoid, finalize; + classify, screen, verify; + screen_sym, screen_min; + permute
             self.launches += (6 if self.screen_flags & 1 else (8 if self.screen_flags & 2 else 9)) if screen else 3
         self.last_screen_stats = screen_stats
@@ -460,8 +477,8 @@ class Lifter:
                 raise ValueError("box_search: a batch must not mix KITTI (y up) with nuScenes/Waymo (z up) frames")
             up_axis = 1 if pb.any_kitti else 2
             box = self._buf(I * 8, torch.float32)
-            self._call("box_search", "cm3d_box_search", _ptr(seg_xyzw), seg_cap, _ptr(o("seg_off")), I, up_axis,
-                       int(box_search), 1, _ptr(box), _ptr(o("errflags")), st)
+            self._call("box_search", "cm3d_box_search", _ptr(seg_xyzw), seg_cap, _ptr(op("seg_off")), I, up_axis,
+                       int(box_search), 1, _ptr(box), _ptr(op("errflags")), st)
             self.launches += 1
         return DeviceOutputs(db, out, lay, seg_cap, seg_point_idx, seg_xyzw, None, None, None,
                              None, col_sums, None, None, None, None, box, None)
