@@ -19,7 +19,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from .quat import Quaternion
+from .quat import Quaternion, quats_from_matrices
 
 ATTRIBUTE_NAMES = {     # src/nuscenes/2d_to_3d.py:70-81
     "barrier": "", "traffic_cone": "", "bicycle": "cycle.without_rider", "motorcycle": "cycle.without_rider",
@@ -165,6 +165,49 @@ def nuscenes_box(sample_token: str, label: str, score, centroid: np.ndarray, lan
         "detection_score": score,
         "attribute_name": attribute_names[detection_name],
     }
+
+
+def nuscenes_boxes(sample_tokens: Sequence[str], labels: Sequence[str], scores: Sequence, centroids: np.ndarray, lane_yaws,
+                   shape_priors: dict, pose_translations: np.ndarray, attribute_names: dict = ATTRIBUTE_NAMES) -> List[dict]:
+    """`nuscenes_box` over all K boxes of a scene at once (the reference's per-box loop nuscenes:745-817 costs
+    ~0.2 ms of interpreter time per box): the same numpy / scipy element operations on arrays, so the
+    results are the per-box ones bit for bit (tests/test_host_logic.py).  `centroids` (K,3) float32,
+    `lane_yaws` (K,) float32, `pose_translations` (K,3) the lidar ego_pose translation of each box's sample."""
+    from scipy.spatial.transform import Rotation as R
+    k = len(labels)
+    if k == 0:
+        return []
+    names = [get_detection_name(l) for l in labels]
+    extents = [get_shape_prior(shape_priors, n) for n in names]
+    veh = np.fromiter((n in VEHICLE_NAMES for n in names), dtype=bool, count=k)
+    c32 = np.asarray(centroids, dtype=np.float32).reshape(k, 3)
+    yaw = np.asarray(lane_yaws)
+    cs, sn = np.cos(yaw), np.sin(yaw)                       # float32, like the scalars of :788-789
+    mats = np.tile(np.eye(3), (k, 1, 1))
+    mats[veh, 0, 0] = cs[veh]
+    mats[veh, 0, 1] = -sn[veh]
+    mats[veh, 1, 0] = sn[veh]
+    mats[veh, 1, 1] = cs[veh]
+    quats = quats_from_matrices(mats)
+    trans = c32.astype(np.float64)
+    if veh.any():
+        c = trans[veh]
+        ego = c - np.asarray(pose_translations, dtype=np.float64).reshape(k, 3)[veh]
+        ext = np.asarray([extents[i][:2] for i in np.flatnonzero(veh)], dtype=np.float64)
+        l, w = ext[:, 0], ext[:, 1]
+        theta = -R.from_quat(quats[veh]).as_euler("xyz", degrees=False)[:, 0]
+        theta = np.where(np.isnan(theta), 0.5 * np.pi, theta)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            alpha = np.arctan(np.abs(ego[:, 1]) / np.abs(ego[:, 0]))
+            alpha = np.where(ego[:, 0] < 0, np.where(ego[:, 1] < 0, -np.pi + alpha, np.pi - alpha),
+                             np.where(ego[:, 1] < 0, -alpha, alpha))
+            offset = np.minimum(np.abs(w / (2 * np.sin(theta - alpha))), np.abs(l / (2 * np.cos(theta - alpha))))
+            trans[veh, 0] = c[:, 0] + offset * np.cos(alpha)
+            trans[veh, 1] = c[:, 1] + offset * np.sin(alpha)
+    trans, quats = trans.tolist(), quats.tolist()
+    return [{"sample_token": sample_tokens[i], "translation": trans[i], "size": list(extents[i]), "rotation": quats[i],
+             "velocity": [0, 0], "detection_name": names[i], "detection_score": scores[i],
+             "attribute_name": attribute_names[names[i]]} for i in range(k)]
 
 
 def nms_predictions(predictions: dict, threshs_by_label: dict = THRESHS_BY_LABEL) -> dict:

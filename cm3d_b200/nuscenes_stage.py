@@ -193,6 +193,7 @@ def scene_boxes(scene: dict, lane_pt_list, cfg, shape_priors: dict, timer) -> Di
     yaw_list, min_distance_list, _ = B.lane_yaws_distances_and_coords(scene["centroids"], lane_pt_list, cfg.DEVICE)
     timer["closest lane"] += time.time() - t0
     where = {cid: k for k, cid in enumerate(scene["centroid_ids"])}
+    toks, labels, scores, ks, poses = [], [], [], [], []
     id_offset = -1
     for tok, data, pose in zip(scene["samples"], scene["data"], scene["lidar_pose"]):
         for label, score, c in zip(data["labels"], data["detection_scores"], data["cam_nums"]):
@@ -200,8 +201,17 @@ def scene_boxes(scene: dict, lane_pt_list, cfg, shape_priors: dict, timer) -> Di
             k = where.get(id_offset)
             if k is None:
                 continue
-            results[tok].append(B.nuscenes_box(tok, label, score, scene["centroids"][k], yaw_list[k], shape_priors,
-                                               pose, cfg.ATTRIBUTE_NAMES))
+            toks.append(tok)
+            labels.append(label)
+            scores.append(score)
+            ks.append(k)
+            poses.append(pose["translation"])
+    t0 = time.time()
+    ks = np.asarray(ks, dtype=np.int64)
+    for box in B.nuscenes_boxes(toks, labels, scores, scene["centroids"][ks], np.asarray(yaw_list)[ks], shape_priors,
+                                np.asarray(poses, dtype=np.float64).reshape(-1, 3), cfg.ATTRIBUTE_NAMES):
+        results[box["sample_token"]].append(box)
+    timer["boxes"] = timer.get("boxes", 0.0) + time.time() - t0
     return results
 
 

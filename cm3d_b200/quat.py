@@ -91,3 +91,20 @@ def _from_matrix(matrix: np.ndarray, rtol=1e-05, atol=1e-08) -> np.ndarray:
     q = np.array(q).astype("float64")
     q *= 0.5 / sqrt(t)
     return q
+
+
+def quats_from_matrices(mats: np.ndarray) -> np.ndarray:
+    """`_from_matrix` over a stack of proper rotation matrices (K,3,3) -> (K,4) (w,x,y,z): the same four
+    branches and the same arithmetic per element (the validity checks are the caller's)."""
+    m = np.swapaxes(np.asarray(mats, dtype=np.float64)[:, :3, :3], 1, 2)
+    m00, m11, m22 = m[:, 0, 0], m[:, 1, 1], m[:, 2, 2]
+    neg = m22 < 0
+    b0 = neg & (m00 > m11)
+    b1 = neg & ~b0
+    b2 = ~neg & (m00 < -m11)
+    t = np.where(b0, 1 + m00 - m11 - m22, np.where(b1, 1 - m00 + m11 - m22, np.where(b2, 1 - m00 - m11 + m22, 1 + m00 + m11 + m22)))
+    d12, d20, d01 = m[:, 1, 2] - m[:, 2, 1], m[:, 2, 0] - m[:, 0, 2], m[:, 0, 1] - m[:, 1, 0]
+    s12, s20, s01 = m[:, 1, 2] + m[:, 2, 1], m[:, 2, 0] + m[:, 0, 2], m[:, 0, 1] + m[:, 1, 0]
+    pick = lambda a, b, c, d: np.where(b0, a, np.where(b1, b, np.where(b2, c, d)))
+    q = np.stack([pick(d12, d20, d01, t), pick(t, s01, s20, d12), pick(s01, t, s12, d20), pick(s20, s12, t, d01)], axis=1)
+    return q * (0.5 / np.sqrt(t))[:, None]
