@@ -237,7 +237,7 @@ def _labels_equal_oracle(gpu, o):
                 bool(np.isnan(cen[~has]).all()))
 
 
-def _disk_leg(frames, lifter, n_sweeps):
+def _disk_leg(frames, lifter, n_sweeps, reader_threads=8):
     """The drop-in nuScenes script (src/nuscenes/2d_to_3d.py -> nuscenes_stage.run) over an on-disk synthetic
     dataset: .bin sweeps, {f}_masks.pkl, {f}_data.json in, pseudolabels JSON out; seconds per frame include
     every file read, the packer, H2D, kernels, pass 2, NMS and the JSON write."""
@@ -257,7 +257,7 @@ def _disk_leg(frames, lifter, n_sweeps):
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         mod.INPUT_PATH, mod.INPUT_DIR, mod.OUTPUT_DIR = os.path.join(work, "nusc"), os.path.join(work, "masks"), os.path.join(work, "out")
-        mod.n_sweeps, mod.BATCH_FRAMES = n_sweeps, 32
+        mod.n_sweeps, mod.BATCH_FRAMES, mod.READER_THREADS = n_sweeps, 32, reader_threads
         import contextlib
         import io
         names = list(scenes)
@@ -270,7 +270,7 @@ def _disk_leg(frames, lifter, n_sweeps):
         n_boxes = sum(len(v) for v in final["results"].values())
         nbytes = sum(os.path.getsize(os.path.join(dp, fn)) for dp, _, fns in os.walk(work) for fn in fns)
         return {"value": n_frames / dt, "unit": UNIT, "frames": n_frames, "scenes": n_scenes, "boxes_after_nms": n_boxes,
-                "dataset_bytes": nbytes, "dataset_write_seconds": round(t_w, 2),
+                "dataset_bytes": nbytes, "dataset_write_seconds": round(t_w, 2), "reader_threads": reader_threads,
                 "note": "src/nuscenes/2d_to_3d.py end to end on an on-disk synthetic nuScenes tree (page-cache warm): devkit record "
                         "lookups, np.fromfile of the sweeps, pickle/json of the masks on reader threads, C packer, H2D, kernels, "
                         "lane lookup, pass 2, circle NMS and the JSON write inside the timed region"}
@@ -633,7 +633,7 @@ def run_ours(args, rank, world, local_rank):
         line["parity_checked"] = parity
         if world == 1 and args.config == "c2" and not args.no_disk_leg:
             try:
-                line["e2e_from_disk"] = _disk_leg(frames, lifter, n_sweeps=10)
+                line["e2e_from_disk"] = _disk_leg(frames, lifter, n_sweeps=10, reader_threads=args.reader_threads)
             except Exception as e:
                 line["e2e_from_disk"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_latency_leg:
@@ -700,6 +700,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame-parallel", action="store_true", help="skip the one-process-per-core CPU baseline")
     ap.add_argument("--no-framespec-leg", action="store_true", help="skip the FrameSpec-level (host packing included) leg")
+    ap.add_argument("--reader-threads", type=int, default=8, help="reader threads of the on-disk script leg")
     ap.add_argument("--no-disk-leg", action="store_true", help="skip the on-disk drop-in script leg")
     ap.add_argument("--no-latency-leg", action="store_true", help="skip the one-frame-per-call latency leg")
     args = ap.parse_args()

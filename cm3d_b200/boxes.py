@@ -114,25 +114,32 @@ def lane_yaws_distances_and_coords(all_centroids, all_lane_pts, device="cuda:0")
 
 
 def circle_nms(dets: np.ndarray, det_labels: Sequence, threshs_by_label: dict) -> List[int]:
-    """Greedy centre-distance NMS, class aware (nuscenes:309-332).  dets rows: x, y, score."""
-    x1, y1, scores = dets[:, 0], dets[:, 1], dets[:, 2]
-    order = scores.argsort()[::-1].astype(np.int32)
-    ndets = dets.shape[0]
-    suppressed = np.zeros(ndets, dtype=np.int32)
-    keep = []
-    for _i in range(ndets):
-        i = order[_i]
-        if suppressed[i] == 1:
-            continue
-        keep.append(i)
-        for _j in range(_i + 1, ndets):
-            j = order[_j]
-            if suppressed[j] == 1:
-                continue
-            dist = (x1[i] - x1[j]) ** 2 + (y1[i] - y1[j]) ** 2
-            if dist <= threshs_by_label[det_labels[j]] and det_labels[j] == det_labels[i]:
-                suppressed[j] = 1
-    return keep
+    """Greedy centre-distance NMS, class aware (nuscenes:309-332, CenterPoint's circle NMS).  dets rows: x, y, score.
+
+    The reference walks all ordered pairs in Python; a box can only suppress boxes of its own class, so the
+    classes are independent greedy passes: per class, in descending score order (the reference's
+    `argsort()[::-1]`, ties included), a surviving box removes every later one within the class radius with one
+    array comparison.  Returns the kept indices in descending score order, like the reference."""
+    dets = np.asarray(dets)
+    n = dets.shape[0]
+    if n == 0:
+        return []
+    order = dets[:, 2].argsort()[::-1]
+    rank = np.empty(n, dtype=np.int64)
+    rank[order] = np.arange(n)
+    labels = np.asarray(det_labels, dtype=object)
+    alive = np.ones(n, dtype=bool)
+    for label in dict.fromkeys(det_labels):
+        idx = order[labels[order] == label]              # this class, best score first
+        x, y, thr = dets[idx, 0], dets[idx, 1], threshs_by_label[label]
+        live = np.ones(idx.size, dtype=bool)
+        for a in range(idx.size - 1):
+            if live[a]:
+                d = (x[a] - x[a + 1:]) ** 2 + (y[a] - y[a + 1:]) ** 2
+                live[a + 1:] &= ~(d <= thr)
+        alive[idx[~live]] = False
+    keep = np.flatnonzero(alive)
+    return [int(k) for k in keep[np.argsort(rank[keep])]]
 
 
 def lane_align_matrix(lane_yaw) -> np.ndarray:

@@ -53,6 +53,7 @@ pointsensor_channel = "LIDAR_TOP"
 SPLIT = "mini_val"            # nuscenes.utils.splits list the reference iterates
 OUTPUT_NAME = "pseudolabels_minival.json"
 BATCH_FRAMES = 32             # frames per GPU launch sequence (not in the reference)
+READER_THREADS = 8            # threads that read sweeps / masks ahead of the GPU (not in the reference)
 
 
 def main(nusc=None, nusc_map_factory=None, scene_names=None, lifter=None):
@@ -63,6 +64,7 @@ def main(nusc=None, nusc_map_factory=None, scene_names=None, lifter=None):
                          CAM_LIST=CAM_LIST, ATTRIBUTE_NAMES=ATTRIBUTE_NAMES, DEVICE=DEVICE, min_dist=min_dist,
                          floor_thresh=floor_thresh, ratio=ratio, n_sweeps=n_sweeps,
                          pointsensor_channel=pointsensor_channel, output_name=OUTPUT_NAME, batch_frames=BATCH_FRAMES,
+                         reader_threads=READER_THREADS,
                          shape_priors_path=os.path.join(os.path.dirname(os.path.abspath(__file__)), "cfg",
                                                         "shape_priors_chatgpt.json"))
     if nusc is None:
