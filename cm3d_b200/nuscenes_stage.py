@@ -135,53 +135,75 @@ def get_all_lane_points_in_scene(nusc_map):
 
 
 def default_map_factory(input_path: str) -> Callable:
+    maps = {}                                                                      # one NuScenesMap per location, not per scene
+
     def factory(nusc, scene):                                                      # nuscenes:216-224
         from nuscenes.map_expansion.map_api import NuScenesMap
         log = nusc.get("log", scene["log_token"])
-        return NuScenesMap(dataroot=input_path, map_name=log["location"])
+        if log["location"] not in maps:
+            maps[log["location"]] = NuScenesMap(dataroot=input_path, map_name=log["location"])
+        return maps[log["location"]]
     return factory
 
 
 # ------------------------------------------------------------------------------------- the stage
-def lift_scene(nusc, scene_name: str, cfg, lifter, timer) -> dict:
-    """Pass 1 of one scene: {"samples": [token...], "data": [data json...], "centroid_ids": [...],
-    "centroids": (K,3) float32, "lidar_pose": [poserecord per frame]}."""
-    scene = nusc.get("scene", nusc.field2token("scene", "name", scene_name)[0])
-    sample = nusc.get("sample", scene["first_sample_token"])
-    num_frames = count_frames(nusc, sample)
-    out = {"samples": [], "data": [], "lidar_pose": [], "centroid_ids": [], "centroids": []}
+def lift_scenes(nusc, scene_items: Sequence[tuple], cfg, lifter, timer):
+    """Pass 1 over the scenes `[(scene_num, scene_name), ...]` through ONE frame stream: the reader threads are
+    already on the next scene's files while the GPU finishes this one.  Yields `(scene_num, scene)` in order as
+    each scene's last frame comes back; scene = {"samples": [token...], "data": [data json...],
+    "centroid_ids": [...], "centroids": (K,3) float32, "lidar_pose": [poserecord per frame]}."""
+    from collections import deque
+    from .lifter import prefetch_map
+    plans, work = [], []
+    for p, (scene_num, scene_name) in enumerate(scene_items):
+        scene = nusc.get("scene", nusc.field2token("scene", "name", scene_name)[0])
+        sample = nusc.get("sample", scene["first_sample_token"])
+        samples = [sample]                              # the scene's sample chain (nuscenes:413-415, :693-694)
+        for _ in range(count_frames(nusc, sample) - 1):
+            samples.append(nusc.get("sample", samples[-1]["next"]))
+        plans.append((scene_num, scene_name, samples))
+        work += [(p, frame_num) for frame_num in range(len(samples))]
+    outs = [{"samples": [], "data": [], "lidar_pose": [], "centroid_ids": [], "centroids": [], "_done": 0, "_ids": 0}
+            for _ in plans]
+    owners = deque()
 
-    samples = [sample]                                  # the scene's sample chain (nuscenes:413-415, :693-694)
-    while len(samples) < num_frames:
-        samples.append(nusc.get("sample", samples[-1]["next"]))
-
-    def build(frame_num):
+    def build(item):
         t0 = time.time()
-        s = samples[frame_num]
-        masks, data = load_frame_masks(cfg.INPUT_DIR, scene_name, frame_num)
+        p, frame_num = item
+        s = plans[p][2][frame_num]
+        masks, data = load_frame_masks(cfg.INPUT_DIR, plans[p][1], frame_num)
         spec = frame_spec(nusc, s, masks, data, cfg)
         ps = nusc.get("sample_data", s["data"][cfg.pointsensor_channel])
-        return spec, s["token"], data, nusc.get("ego_pose", ps["ego_pose_token"]), time.time() - t0
+        return p, spec, s["token"], data, nusc.get("ego_pose", ps["ego_pose_token"]), time.time() - t0
 
     def frames():
-        from .lifter import prefetch_map
-        for spec, token, data, pose, dt in prefetch_map(build, range(num_frames), getattr(cfg, "reader_threads", 8)):
+        for p, spec, token, data, pose, dt in prefetch_map(build, work, getattr(cfg, "reader_threads", 8)):
+            out = outs[p]
             out["samples"].append(token)
             out["data"].append(data)
             out["lidar_pose"].append(pose)
+            owners.append(p)
             timer["io"] += dt
             yield spec
 
-    id_offset = 0
     for res_batch in lifter.lift_frame_stream(frames(), batch_frames=cfg.batch_frames, timer=timer):
         for r in res_batch:
-            for i in range(len(r.medoid_local)):
-                if r.medoid_local[i] >= 0:                  # empty mask -> `continue` (:626-628)
-                    out["centroid_ids"].append(id_offset + i)
-                    out["centroids"].append(r.centroids[i])
-            id_offset += len(r.medoid_local)
-    out["centroids"] = np.asarray(out["centroids"], np.float32).reshape(-1, 3)
-    return out
+            p = owners.popleft()
+            out = outs[p]
+            has = np.flatnonzero(np.asarray(r.medoid_local) >= 0)       # empty mask -> `continue` (:626-628)
+            out["centroid_ids"] += (out["_ids"] + has).tolist()
+            out["centroids"] += [r.centroids[i] for i in has]
+            out["_ids"] += len(r.medoid_local)
+            out["_done"] += 1
+            if out["_done"] == len(plans[p][2]):
+                out["centroids"] = np.asarray(out["centroids"], np.float32).reshape(-1, 3)
+                del out["_done"], out["_ids"]
+                yield plans[p][0], out
+
+
+def lift_scene(nusc, scene_name: str, cfg, lifter, timer) -> dict:
+    """Pass 1 of one scene (see `lift_scenes`)."""
+    return next(lift_scenes(nusc, [(0, scene_name)], cfg, lifter, timer))[1]
 
 
 def scene_boxes(scene: dict, lane_pt_list, cfg, shape_priors: dict, timer) -> Dict[str, list]:
@@ -229,15 +251,14 @@ def run(cfg, nusc, nusc_map_factory: Callable, scene_names: Sequence[str], lifte
         shape_priors = json.load(f)
     predictions = {"meta": {"use_camera": True, "use_lidar": False, "use_radar": False, "use_map": True,
                             "use_external": False}, "results": {}}
-    local = {}
-    for scene_num, scene_name in enumerate(scene_names):
-        if scene_num % world != rank:
-            continue
-        scene_rec = nusc.get("scene", nusc.field2token("scene", "name", scene_name)[0])
+    local, lanes = {}, {}
+    items = [(scene_num, scene_name) for scene_num, scene_name in enumerate(scene_names) if scene_num % world == rank]
+    for scene_num, scene in lift_scenes(nusc, items, cfg, lifter, timer):
+        scene_rec = nusc.get("scene", nusc.field2token("scene", "name", scene_names[scene_num])[0])
         nusc_map = nusc_map_factory(nusc, scene_rec)
-        _, lane_pt_list = get_all_lane_points_in_scene(nusc_map)
-        scene = lift_scene(nusc, scene_name, cfg, lifter, timer)
-        local[scene_num] = scene_boxes(scene, lane_pt_list, cfg, shape_priors, timer)
+        if id(nusc_map) not in lanes:                   # discretised once per map object (the factory keeps one per location)
+            lanes = {id(nusc_map): (nusc_map, get_all_lane_points_in_scene(nusc_map)[1])}
+        local[scene_num] = scene_boxes(scene, lanes[id(nusc_map)][1], cfg, shape_priors, timer)
     merged = gather_labels(local, len(scene_names)) if world > 1 else [local.get(i) for i in range(len(scene_names))]
     if rank != 0:
         return {}

@@ -221,6 +221,50 @@ def test_oracle_reproduces_reference_waymo_run(tmp_path):
 
 
 # ------------------------------------------------------------------------------------- GPU: drop-in scripts == reference run
+def test_nuscenes_stage_host_logic_reproduces_reference_run(tmp_path, monkeypatch):
+    """The nuScenes stage's HOST side on the CPU - one frame stream chained over the scenes, instance ids, the
+    vectorised pass 2, circle NMS, the JSON file - with the CPU oracle standing in for the two GPU calls
+    (`Lifter.lift_frame_stream`, `cm3d_nearest_lane`): what it writes equals what the reference script wrote."""
+    from types import SimpleNamespace
+    from cm3d_b200 import boxes as B
+    from oracle import ref_boxes as RB
+    from oracle import ref_lift as RL
+    from oracle.refrun import make as M
+    fix = _fixture("nuscenes")
+    scenes = M.nuscenes_scenes()
+    nusc, map_factory, root, input_dir = M.write_nuscenes_tree(str(tmp_path), scenes)
+
+    class OracleLifter:
+        batches = []
+
+        def lift_frame_stream(self, frames, batch_frames=32, timer=None):
+            batch = []
+            for spec in frames:
+                r = RL.lift_frame(spec, record_pix=False)
+                batch.append(SimpleNamespace(medoid_local=np.asarray(r["medoid_local"]),
+                                             centroids=np.asarray(r["centroids"], np.float32)))
+                if len(batch) == batch_frames:
+                    self.batches.append(len(batch))
+                    yield batch
+                    batch = []
+            if batch:
+                self.batches.append(len(batch))
+                yield batch
+
+    monkeypatch.setattr(B, "lane_yaws_distances_and_coords",
+                        lambda cents, lanes, device=None: RB.lane_yaws_distances_and_coords(cents, lanes)[:3])
+    out_dir = str(tmp_path / "out")
+    mod = _load_script("src/nuscenes/2d_to_3d.py", "nusc_2d_to_3d_host")
+    mod.INPUT_PATH, mod.INPUT_DIR, mod.OUTPUT_DIR, mod.BATCH_FRAMES, mod.READER_THREADS = root, input_dir, out_dir, 3, 2
+    mod.DEVICE = "cuda:0"                # a name only: both GPU calls are replaced above, nothing else touches CUDA
+    lifter = OracleLifter()
+    mod.main(nusc, map_factory, list(scenes), lifter=lifter)
+    n_frames = sum(len(fs) for fs in scenes.values())
+    assert sum(lifter.batches) == n_frames and len(lifter.batches) == -(-n_frames // 3)     # batches span the scenes
+    got = json.load(open(os.path.join(out_dir, "pseudolabels_minival.json")))
+    _cmp_nuscenes(got, fix, rot_tol=1e-7, trans_tol=0.0)
+
+
 @pytest.mark.gpu
 def test_nuscenes_script_reproduces_reference_run(tmp_path):
     from oracle.refrun import make as M
