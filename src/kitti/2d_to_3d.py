@@ -43,7 +43,7 @@ NUM_SAMPLES = None            # None = the reference's hard-coded 7481 (training
 BATCH_FRAMES = 64
 
 
-def main(kitti=None, frame_range=None):
+def main(kitti=None, frame_range=None, lifter=None):
     from cm3d_b200 import kitti_stage as stage
     if DEVICE == "cpu":
         raise RuntimeError("cm3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -53,7 +53,7 @@ def main(kitti=None, frame_range=None):
                          batch_frames=BATCH_FRAMES,
                          shape_priors_path=os.path.join(os.path.dirname(os.path.abspath(__file__)), "cfg",
                                                         "shape_priors_chatgpt.json"))
-    return stage.run(cfg, kitti, frame_range)
+    return stage.run(cfg, kitti, frame_range, lifter=lifter)
 
 
 if __name__ == "__main__":

@@ -54,7 +54,7 @@ def _tfrecord_scenes(scene_names):
         yield scene_name, frames_of(scene_name)
 
 
-def main(scenes=None, points_fn=None):
+def main(scenes=None, points_fn=None, lifter=None):
     from cm3d_b200 import waymo_stage as stage
     if DEVICE == "cpu":
         raise RuntimeError("cm3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -67,7 +67,7 @@ def main(scenes=None, points_fn=None):
         scene_list = sorted(os.listdir(INPUT_PATH))
         print(len(scene_list))
         scenes = _tfrecord_scenes(scene_list[SCENE_SLICE[0]:SCENE_SLICE[1]])
-    return stage.run(cfg, scenes, points_fn)
+    return stage.run(cfg, scenes, points_fn, lifter=lifter)
 
 
 if __name__ == "__main__":

@@ -220,44 +220,60 @@ def test_oracle_reproduces_reference_waymo_run(tmp_path):
     _cmp_waymo(expect, want, xyz_tol=1e-3, head_tol=1e-6)
 
 
-# ------------------------------------------------------------------------------------- GPU: drop-in scripts == reference run
+# ------------------------------------------------------------------------------------- CPU: the stages' host logic
+class _OracleLifter:
+    """Stand-in for `Lifter` in the host-logic tests below: the CPU oracle per frame, results shaped like LiftResult
+    (`counts`, `medoid_local`, `centroids`, `yaw`), handed back in batches like `lift_frame_stream` does."""
+
+    def __init__(self):
+        self.batches = []
+
+    def lift_frame_stream(self, frames, batch_frames=32, timer=None):
+        from types import SimpleNamespace
+        from oracle import obb_oracle as O
+        from oracle import ref_lift as RL
+        batch = []
+        for spec in frames:
+            r = RL.lift_frame(spec, record_pix=False)
+            counts = np.array([len(ix) for ix in r["idx"]], np.int64)
+            yaw = np.full(len(counts), np.nan)
+            if spec.dataset == "kitti":
+                aggr = np.asarray(r["aggr"]).reshape(-1, 3)
+                for i, ix in enumerate(r["idx"]):
+                    if len(ix) > 3:
+                        yaw[i] = O.yaw_of(np.asarray(O.get_depth_bbox_or_fallback(aggr[np.asarray(ix)])[2], np.float64))
+            batch.append(SimpleNamespace(counts=counts, medoid_local=np.asarray(r["medoid_local"]), yaw=yaw,
+                                         centroids=np.asarray(r["centroids"], np.float32).reshape(len(counts), -1)[:, :3]))
+            if len(batch) == batch_frames:
+                self.batches.append(len(batch))
+                yield batch
+                batch = []
+        if batch:
+            self.batches.append(len(batch))
+            yield batch
+
+
+def _oracle_lane_lookup(monkeypatch):
+    from cm3d_b200 import boxes as B
+    from oracle import ref_boxes as RB
+    monkeypatch.setattr(B, "lane_yaws_distances_and_coords",
+                        lambda cents, lanes, device=None: RB.lane_yaws_distances_and_coords(cents, lanes)[:3])
+
+
 def test_nuscenes_stage_host_logic_reproduces_reference_run(tmp_path, monkeypatch):
     """The nuScenes stage's HOST side on the CPU - one frame stream chained over the scenes, instance ids, the
     vectorised pass 2, circle NMS, the JSON file - with the CPU oracle standing in for the two GPU calls
     (`Lifter.lift_frame_stream`, `cm3d_nearest_lane`): what it writes equals what the reference script wrote."""
-    from types import SimpleNamespace
-    from cm3d_b200 import boxes as B
-    from oracle import ref_boxes as RB
-    from oracle import ref_lift as RL
     from oracle.refrun import make as M
     fix = _fixture("nuscenes")
     scenes = M.nuscenes_scenes()
     nusc, map_factory, root, input_dir = M.write_nuscenes_tree(str(tmp_path), scenes)
-
-    class OracleLifter:
-        batches = []
-
-        def lift_frame_stream(self, frames, batch_frames=32, timer=None):
-            batch = []
-            for spec in frames:
-                r = RL.lift_frame(spec, record_pix=False)
-                batch.append(SimpleNamespace(medoid_local=np.asarray(r["medoid_local"]),
-                                             centroids=np.asarray(r["centroids"], np.float32)))
-                if len(batch) == batch_frames:
-                    self.batches.append(len(batch))
-                    yield batch
-                    batch = []
-            if batch:
-                self.batches.append(len(batch))
-                yield batch
-
-    monkeypatch.setattr(B, "lane_yaws_distances_and_coords",
-                        lambda cents, lanes, device=None: RB.lane_yaws_distances_and_coords(cents, lanes)[:3])
+    _oracle_lane_lookup(monkeypatch)
     out_dir = str(tmp_path / "out")
     mod = _load_script("src/nuscenes/2d_to_3d.py", "nusc_2d_to_3d_host")
     mod.INPUT_PATH, mod.INPUT_DIR, mod.OUTPUT_DIR, mod.BATCH_FRAMES, mod.READER_THREADS = root, input_dir, out_dir, 3, 2
     mod.DEVICE = "cuda:0"                # a name only: both GPU calls are replaced above, nothing else touches CUDA
-    lifter = OracleLifter()
+    lifter = _OracleLifter()
     mod.main(nusc, map_factory, list(scenes), lifter=lifter)
     n_frames = sum(len(fs) for fs in scenes.values())
     assert sum(lifter.batches) == n_frames and len(lifter.batches) == -(-n_frames // 3)     # batches span the scenes
@@ -265,6 +281,45 @@ def test_nuscenes_stage_host_logic_reproduces_reference_run(tmp_path, monkeypatc
     _cmp_nuscenes(got, fix, rot_tol=1e-7, trans_tol=0.0)
 
 
+def test_kitti_stage_host_logic_reproduces_reference_run(tmp_path):
+    """KITTI stage host side (file truncation, M <= 3 skip, NaN-yaw fallback, prior shuffle, the label line) with the
+    oracle standing in for the GPU: the pred/ and pseudo/ files equal the reference script's."""
+    from oracle.refrun import make as M
+    fix = _fixture("kitti")
+    frames = M.kitti_frames()
+    root, input_dir = M.write_kitti_tree(str(tmp_path), frames)
+    pred_dir, pseudo_dir = str(tmp_path / "pred"), str(tmp_path / "pseudo")
+    os.makedirs(pred_dir)
+    with open(os.path.join(pred_dir, "000001.txt"), "w") as f:
+        f.write("stale line from an earlier run\n")
+    mod = _load_script("src/kitti/2d_to_3d.py", "kitti_2d_to_3d_host")
+    mod.INPUT_PATH, mod.INPUT_DIR, mod.PRED_DIR, mod.PSEUDO_DIR = root, input_dir, pred_dir, pseudo_dir
+    mod.NUM_SAMPLES, mod.BATCH_FRAMES, mod.DEVICE = len(frames), 2, "cuda:0"
+    written = mod.main(lifter=_OracleLifter())
+    files = {}
+    for d, p in (("pred", pred_dir), ("pseudo", pseudo_dir)):
+        for k in range(len(frames)):
+            files[f"{d}/{k:06}.txt"] = open(os.path.join(p, f"{k:06}.txt")).read().splitlines()
+    assert written == _cmp_kitti(files, fix, yaw_tol=1e-9) // 2
+
+
+def test_waymo_stage_host_logic_reproduces_reference_run(tmp_path, monkeypatch):
+    """Waymo stage host side (missing mask files, vehicle -> global, lanes of frame 0, pass 2, per-timestamp NMS,
+    the metrics.Objects wire format) with the oracle standing in for the GPU: equals the reference script's .bin."""
+    from oracle.refrun import make as M
+    fix = _fixture("waymo")
+    scenes = M.waymo_scenes()
+    scene_frames, _, input_dir = M.write_waymo_tree(str(tmp_path), scenes)
+    _oracle_lane_lookup(monkeypatch)
+    mod = _load_script("src/waymo/2d_to_3d.py", "waymo_2d_to_3d_host")
+    mod.INPUT_DIR, mod.OUTPUT_FILE, mod.BATCH_FRAMES, mod.DEVICE = input_dir, str(tmp_path / "out" / "pred.bin"), 2, "cuda:0"
+    mod.main(scene_frames, lambda fr: fr.points_vehicle, lifter=_OracleLifter())
+    got = _parse_waymo(open(mod.OUTPUT_FILE, "rb").read())
+    want = _parse_waymo(open(os.path.join(GOLD, fix["bin"]), "rb").read())
+    _cmp_waymo(got, want, xyz_tol=1e-3, head_tol=1e-6)
+
+
+# ------------------------------------------------------------------------------------- GPU: drop-in scripts == reference run
 @pytest.mark.gpu
 def test_nuscenes_script_reproduces_reference_run(tmp_path):
     from oracle.refrun import make as M
