@@ -87,6 +87,23 @@ def _f32(a):
     return np.asarray(a, dtype=np.float64).astype(np.float32)
 
 
+_ROT = {}
+
+
+def _rot32(rotation, transpose=False) -> np.ndarray:
+    """float32 of `Quaternion(rotation).rotation_matrix` (or its transpose).  A scene's calibrated_sensor records
+    repeat for every sweep and camera of every frame, so the matrices are kept by quaternion value."""
+    key = (tuple(rotation), transpose)
+    m = _ROT.get(key)
+    if m is None:
+        if len(_ROT) > 8192:
+            _ROT.clear()
+        m = Quaternion(rotation).rotation_matrix
+        m = _ROT[key] = _f32(m.T if transpose else m)
+        m.setflags(write=False)
+    return m
+
+
 def frame_spec(nusc, sample, masks: List[RLEMask], data: dict, cfg) -> FrameSpec:
     """Everything nuscenes:430-503 and the per-mask constants of :569-587 read from the devkit."""
     pointsensor_next = nusc.get("sample_data", sample["data"][cfg.pointsensor_channel])
@@ -95,9 +112,9 @@ def frame_spec(nusc, sample, masks: List[RLEMask], data: dict, cfg) -> FrameSpec
         sweeps.append(load_lidar_bin(os.path.join(nusc.dataroot, pointsensor_next["filename"])))
         cs_record = nusc.get("calibrated_sensor", pointsensor_next["calibrated_sensor_token"])
         poserecord = nusc.get("ego_pose", pointsensor_next["ego_pose_token"])
-        sweep_ops.append([op_R(_f32(Quaternion(cs_record["rotation"]).rotation_matrix)),      # :451-457
+        sweep_ops.append([op_R(_rot32(cs_record["rotation"])),                                   # :451-457
                           op_T(_f32(np.array(cs_record["translation"]))),
-                          op_R(_f32(Quaternion(poserecord["rotation"]).rotation_matrix)),
+                          op_R(_rot32(poserecord["rotation"])),
                           op_T(_f32(np.array(poserecord["translation"])))])
         try:
             pointsensor_next = nusc.get("sample_data", pointsensor_next["next"])  # :460-463
@@ -112,9 +129,9 @@ def frame_spec(nusc, sample, masks: List[RLEMask], data: dict, cfg) -> FrameSpec
         K = _f32(np.array(cs_record["camera_intrinsic"])) * ratio32               # :585-587
         K[2, 2] = 1
         cams.append(CamSpec([op_T(_f32(-np.array(poserecord["translation"]))),    # :569-577
-                             op_R(_f32(Quaternion(poserecord["rotation"]).rotation_matrix.T)),
+                             op_R(_rot32(poserecord["rotation"], True)),
                              op_T(_f32(-np.array(cs_record["translation"]))),
-                             op_R(_f32(Quaternion(cs_record["rotation"]).rotation_matrix.T))], K))
+                             op_R(_rot32(cs_record["rotation"], True))], K))
     n = len(data["labels"])
     return FrameSpec("nuscenes", sweeps, sweep_ops, cams, np.asarray(data["cam_nums"][:n], np.int32), masks[:n],
                      list(data["labels"]), list(data["detection_scores"]), fourth=FOURTH_COL3,
