@@ -344,19 +344,21 @@ def run_ours(args, rank, world, local_rank):
     import collections
     # the last eight steps' buffers stay referenced (as in the streaming path's pipeline): a workspace that is
     # freed while the other stream still uses it cannot be reused, and the allocator would cudaMalloc a new one
-    ring = collections.deque(maxlen=8 if overlap else 1)
-    for w in range(9):
+    ring = collections.deque(maxlen=max(1, args.ring) if overlap else 1)
+    for w in range(ring.maxlen + 1):
         with torch.cuda.stream(front):
             ring.append(lifter.run(dbs[w % n_res], seg_cap=seg_cap, overlap=overlap))
     barrier()
     e0.record(cur)
     front.wait_stream(cur)
+    t_host = time.perf_counter()
     with torch.cuda.stream(front):
         for k in range(args.steps):
             if overlap and len(ring) == ring.maxlen:
                 ring[0].done.synchronize()      # the host stays at most eight steps ahead (the GPU always has work queued):
                 #                                 buffers are then freed AFTER their last use and recycled without cudaMalloc
             ring.append(lifter.run(dbs[k % n_res], seg_cap=seg_cap, overlap=overlap))
+    t_host = (time.perf_counter() - t_host) / args.steps * 1e3
     do = ring[-1]
     if overlap:
         cur.wait_event(do.done)             # the medoid stream is in order: the last step's event covers every step
@@ -590,6 +592,7 @@ def run_ours(args, rank, world, local_rank):
                     "capacity_retries": e2e_retries_all,
                     "api": "Lifter.lift_packed_stream (pinned host buffers in, label block out), distinct batches, the lifter's own capacity estimate"},
             "gpu_launches": launches,
+            "host_ms_per_step_rank0": round(t_host, 3),      # launch-side time of a step in the device-timed loop
             "e2e_from_framespecs": None if fs is None else {
                 "value": fs_frames_all / (fs_ms * 1e-3), "unit": UNIT, "frames": fs_frames_all, "seconds": fs_ms * 1e-3,
                 "distinct_frames_per_gpu": n_stream, "cycles": fs["cycles"], "capacity_retries": fs_retries_all,
@@ -700,6 +703,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame-parallel", action="store_true", help="skip the one-process-per-core CPU baseline")
     ap.add_argument("--no-framespec-leg", action="store_true", help="skip the FrameSpec-level (host packing included) leg")
+    ap.add_argument("--ring", type=int, default=3, help="steps the host may run ahead of the GPU in the device-timed loop")
     ap.add_argument("--reader-threads", type=int, default=8, help="reader threads of the on-disk script leg")
     ap.add_argument("--no-disk-leg", action="store_true", help="skip the on-disk drop-in script leg")
     ap.add_argument("--no-latency-leg", action="store_true", help="skip the one-frame-per-call latency leg")
