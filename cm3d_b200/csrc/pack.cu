@@ -61,6 +61,32 @@ void pack_rows(float *dst, const float *src, int64_t n, int stride_in, int cols)
         int64_t k = 0;
         if (cols == 4) {
             for (; k < n; ++k) _mm_stream_ps(dst + 4 * k, _mm_loadu_ps(src + (int64_t)stride_in * k));
+        } else if (stride_in == 5) {            // (N,5) rows -> x, y, z: five loads, four shuffles, three stores per 4 rows
+            for (; k + 4 <= n; k += 4) {
+                const float *p = src + 5 * k;
+                const __m128 v0 = _mm_loadu_ps(p), v1 = _mm_loadu_ps(p + 4), v2 = _mm_loadu_ps(p + 8),
+                             v3 = _mm_loadu_ps(p + 12), v4 = _mm_loadu_ps(p + 16);
+                const __m128 t = _mm_shuffle_ps(v0, v1, _MM_SHUFFLE(1, 1, 2, 2));                 // f2 f2 f5 f5
+                _mm_stream_ps(dst + 3 * k, _mm_shuffle_ps(v0, t, _MM_SHUFFLE(2, 0, 1, 0)));       // f0 f1 f2 f5
+                _mm_stream_ps(dst + 3 * k + 4, _mm_shuffle_ps(v1, v2, _MM_SHUFFLE(3, 2, 3, 2)));  // f6 f7 f10 f11
+                _mm_stream_ps(dst + 3 * k + 8, _mm_shuffle_ps(v3, v4, _MM_SHUFFLE(1, 0, 3, 0)));  // f12 f15 f16 f17
+            }
+        } else if (stride_in == 3) {            // (N,3) rows as they are (Waymo's range-image points)
+            const int64_t m = 3 * n;
+            int64_t j = 0;
+            for (; j + 4 <= m; j += 4) _mm_stream_ps(dst + j, _mm_loadu_ps(src + j));
+            for (; j < m; ++j) dst[j] = src[j];
+            k = n;
+        } else if (stride_in == 4) {            // (N,4) rows -> x, y, z
+            for (; k + 4 <= n; k += 4) {
+                const float *p = src + 4 * k;
+                const __m128 a = _mm_loadu_ps(p), b = _mm_loadu_ps(p + 4), c = _mm_loadu_ps(p + 8), d = _mm_loadu_ps(p + 12);
+                const __m128 t = _mm_shuffle_ps(a, b, _MM_SHUFFLE(0, 0, 2, 2));                   // a2 a2 b0 b0
+                const __m128 u = _mm_shuffle_ps(c, d, _MM_SHUFFLE(0, 0, 2, 2));                   // c2 c2 d0 d0
+                _mm_stream_ps(dst + 3 * k, _mm_shuffle_ps(a, t, _MM_SHUFFLE(2, 0, 1, 0)));        // a0 a1 a2 b0
+                _mm_stream_ps(dst + 3 * k + 4, _mm_shuffle_ps(b, c, _MM_SHUFFLE(1, 0, 2, 1)));    // b1 b2 c0 c1
+                _mm_stream_ps(dst + 3 * k + 8, _mm_shuffle_ps(u, d, _MM_SHUFFLE(2, 1, 2, 0)));    // c2 d0 d1 d2
+            }
         } else {
             for (; k + 4 <= n; k += 4) {
                 const float *a = src + (int64_t)stride_in * k, *b = a + stride_in, *c = b + stride_in, *d = c + stride_in;
@@ -68,6 +94,8 @@ void pack_rows(float *dst, const float *src, int64_t n, int stride_in, int cols)
                 _mm_stream_ps(dst + 3 * k + 4, _mm_setr_ps(b[1], b[2], c[0], c[1]));
                 _mm_stream_ps(dst + 3 * k + 8, _mm_setr_ps(c[2], d[0], d[1], d[2]));
             }
+        }
+        if (cols != 4) {
             for (; k < n; ++k) memcpy(dst + 3 * k, src + (int64_t)stride_in * k, 12);
         }
         _mm_sfence();
