@@ -516,12 +516,13 @@ def run_ours(args, rank, world, local_rank):
         hbm_k = max((k for k in kern if k in ("aggregate", "project_count", "compact")), key=lambda k: kern[k]["ms"])
         traffic, traffic_src, erode_dram = None, None, None
         try:        # DRAM bytes per launch from the newest committed ncu capture of this same command
-            cands = sorted(fn for fn in os.listdir(os.path.join(ROOT, "profiles")) if fn.endswith("_traffic.json"))
-            with open(os.path.join(ROOT, "profiles", cands[-1])) as f:
-                tj = json.load(f)
-            if tj.get("frames_per_launch") == B and tj.get("config", "c2") == args.config:
-                traffic, traffic_src = tj["dram_bytes_per_launch"].get("k_" + hbm_k), tj["source"]
-                erode_dram = tj["dram_bytes_per_launch"].get("k_erode3x3")
+            for fn in sorted((fn for fn in os.listdir(os.path.join(ROOT, "profiles")) if fn.endswith("_traffic.json")), reverse=True):
+                with open(os.path.join(ROOT, "profiles", fn)) as f:
+                    tj = json.load(f)
+                if tj.get("frames_per_launch") == B and tj.get("config", "c2") == args.config:
+                    traffic, traffic_src = tj["dram_bytes_per_launch"].get("k_" + hbm_k), tj["source"]
+                    erode_dram = tj["dram_bytes_per_launch"].get("k_erode3x3")
+                    break
         except Exception:
             pass
         if erode_dram and "masks_erode" in kern:     # rows without set pixels are written unread: report the DRAM rate too

@@ -54,8 +54,12 @@ def launches(path, tag, cmd):
         f.write("kernel,launches,avg_us,share,dram_MB_per_launch\n")
         for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{k},{a[0]},{a[1] / a[0] / 1e3:.1f},{a[1] / tot:.4f},{a[2] / a[0] / 1e6:.1f}\n")
-    tj = {"source": f"profiles/{tag}_ncu_launch_summary.csv (ncu launch list of `{cmd}`, batch 64 C2 frames)",
-          "frames_per_launch": 64, "config": "c2",
+    import re
+    m = re.search(r"--config (c\d)", cmd)
+    config = m.group(1) if m else "c2"
+    batch = {"c1": 64, "c2": 64, "c3": 32, "c4": 16}[config]            # bench.py CONFIGS
+    tj = {"source": f"profiles/{tag}_ncu_launch_summary.csv (ncu launch list of `{cmd}`, batch {batch} {config.upper()} frames)",
+          "frames_per_launch": batch, "config": config,
           "dram_bytes_per_launch": {k.replace("cm3d::", ""): int(a[2] / a[0]) for k, a in agg.items() if k.startswith("cm3d::")}}
     with open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w") as f:
         json.dump(tj, f, indent=1)
