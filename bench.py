@@ -208,7 +208,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "frames_per_step": nf, "mask_input": MASK_INPUT},
+        "config": {"workload": cfg["workload"], "mask_input": MASK_INPUT},         # our arm's workload, a bounded sample of it per step
+        "run": {"frames_per_step": nf, "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -577,15 +578,15 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "frames_per_gpu_per_step": B, "mask_input": MASK_INPUT,
-                       "distinct_resident_batches_per_gpu": n_res, "distinct_frames_per_gpu": n_stream,
-                       "points_per_step": int(npts), "member_points_per_step": int(segt),
-                       "point_columns_shipped": "x, y, z (the 4th column never reaches a label: nuscenes:645,656)",
+            "config": {"workload": cfg["workload"], "mask_input": MASK_INPUT,
                        "l2": f"a step reads one of {n_res} distinct resident batches: {pbs[0].h2d_bytes / 1e6:.0f} MB inputs + {inter_mb:.0f} MB "
                              f"intermediates per step > 126 MB L2, no explicit flush",
-                       "streams": ("front end of step k+1 (high-priority stream) overlaps the medoid of step k (second stream)"
-                                   if overlap else "one stream"),
                        "parallelism": f"frames sharded by sample index, {world} process(es), no collective"},
+            "run": {"frames_per_gpu_per_step": B, "distinct_resident_batches_per_gpu": n_res, "distinct_frames_per_gpu": n_stream,
+                    "points_per_step": int(npts), "member_points_per_step": int(segt),
+                    "point_columns_shipped": "x, y, z (the 4th column never reaches a label: nuscenes:645,656)",
+                    "streams": ("front end of step k+1 (high-priority stream) overlaps the medoid of step k (second stream)"
+                                if overlap else "one stream")},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": d2h_bytes * world, "ms_per_step": e2e_ms / args.steps,
