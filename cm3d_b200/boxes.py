@@ -174,13 +174,46 @@ def nuscenes_box(sample_token: str, label: str, score, centroid: np.ndarray, lan
     }
 
 
+def lane_align_matrices(lane_yaws, where=None) -> np.ndarray:
+    """`lane_align_matrix` for K yaws at once (rows where `where` is False stay the identity)."""
+    yaw = np.asarray(lane_yaws)
+    k = yaw.shape[0]
+    where = np.ones(k, dtype=bool) if where is None else where
+    cs, sn = np.cos(yaw), np.sin(yaw)                       # float32 yaws give float32 values, like the scalars of :788-789
+    mats = np.tile(np.eye(3), (k, 1, 1))
+    mats[where, 0, 0] = cs[where]
+    mats[where, 0, 1] = -sn[where]
+    mats[where, 1, 0] = sn[where]
+    mats[where, 1, 1] = cs[where]
+    return mats
+
+
+def push_centroids(centroids: np.ndarray, ego_centroids: np.ndarray, extents_lw: np.ndarray, quats_wxyz: np.ndarray) -> np.ndarray:
+    """`push_centroid` for K boxes at once: the same scipy / numpy element operations on arrays (bit-identical
+    per box).  `extents_lw[:, 0]` is what the reference calls l (= extents[0]), `[:, 1]` its w."""
+    from scipy.spatial.transform import Rotation as R
+    c = np.asarray(centroids, dtype=np.float64)
+    ego = np.asarray(ego_centroids, dtype=np.float64)
+    l, w = extents_lw[:, 0], extents_lw[:, 1]
+    theta = -R.from_quat(quats_wxyz).as_euler("xyz", degrees=False)[:, 0]      # (w,x,y,z) read as (x,y,z,w), like the reference
+    theta = np.where(np.isnan(theta), 0.5 * np.pi, theta)
+    out = c.copy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        alpha = np.arctan(np.abs(ego[:, 1]) / np.abs(ego[:, 0]))
+        alpha = np.where(ego[:, 0] < 0, np.where(ego[:, 1] < 0, -np.pi + alpha, np.pi - alpha),
+                         np.where(ego[:, 1] < 0, -alpha, alpha))
+        offset = np.minimum(np.abs(w / (2 * np.sin(theta - alpha))), np.abs(l / (2 * np.cos(theta - alpha))))
+        out[:, 0] = c[:, 0] + offset * np.cos(alpha)
+        out[:, 1] = c[:, 1] + offset * np.sin(alpha)
+    return out
+
+
 def nuscenes_boxes(sample_tokens: Sequence[str], labels: Sequence[str], scores: Sequence, centroids: np.ndarray, lane_yaws,
                    shape_priors: dict, pose_translations: np.ndarray, attribute_names: dict = ATTRIBUTE_NAMES) -> List[dict]:
     """`nuscenes_box` over all K boxes of a scene at once (the reference's per-box loop nuscenes:745-817 costs
     ~0.2 ms of interpreter time per box): the same numpy / scipy element operations on arrays, so the
     results are the per-box ones bit for bit (tests/test_host_logic.py).  `centroids` (K,3) float32,
     `lane_yaws` (K,) float32, `pose_translations` (K,3) the lidar ego_pose translation of each box's sample."""
-    from scipy.spatial.transform import Rotation as R
     k = len(labels)
     if k == 0:
         return []
@@ -188,29 +221,14 @@ def nuscenes_boxes(sample_tokens: Sequence[str], labels: Sequence[str], scores: 
     extents = [get_shape_prior(shape_priors, n) for n in names]
     veh = np.fromiter((n in VEHICLE_NAMES for n in names), dtype=bool, count=k)
     c32 = np.asarray(centroids, dtype=np.float32).reshape(k, 3)
-    yaw = np.asarray(lane_yaws)
-    cs, sn = np.cos(yaw), np.sin(yaw)                       # float32, like the scalars of :788-789
-    mats = np.tile(np.eye(3), (k, 1, 1))
-    mats[veh, 0, 0] = cs[veh]
-    mats[veh, 0, 1] = -sn[veh]
-    mats[veh, 1, 0] = sn[veh]
-    mats[veh, 1, 1] = cs[veh]
+    mats = lane_align_matrices(lane_yaws, veh)
     quats = quats_from_matrices(mats)
     trans = c32.astype(np.float64)
     if veh.any():
         c = trans[veh]
         ego = c - np.asarray(pose_translations, dtype=np.float64).reshape(k, 3)[veh]
         ext = np.asarray([extents[i][:2] for i in np.flatnonzero(veh)], dtype=np.float64)
-        l, w = ext[:, 0], ext[:, 1]
-        theta = -R.from_quat(quats[veh]).as_euler("xyz", degrees=False)[:, 0]
-        theta = np.where(np.isnan(theta), 0.5 * np.pi, theta)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            alpha = np.arctan(np.abs(ego[:, 1]) / np.abs(ego[:, 0]))
-            alpha = np.where(ego[:, 0] < 0, np.where(ego[:, 1] < 0, -np.pi + alpha, np.pi - alpha),
-                             np.where(ego[:, 1] < 0, -alpha, alpha))
-            offset = np.minimum(np.abs(w / (2 * np.sin(theta - alpha))), np.abs(l / (2 * np.cos(theta - alpha))))
-            trans[veh, 0] = c[:, 0] + offset * np.cos(alpha)
-            trans[veh, 1] = c[:, 1] + offset * np.sin(alpha)
+        trans[veh] = push_centroids(c, ego, ext, quats[veh])
     trans, quats = trans.tolist(), quats.tolist()
     return [{"sample_token": sample_tokens[i], "translation": trans[i], "size": list(extents[i]), "rotation": quats[i],
              "velocity": [0, 0], "detection_name": names[i], "detection_score": scores[i],

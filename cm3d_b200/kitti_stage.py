@@ -10,7 +10,9 @@ PRED_DIR (with score) and one in PSEUDO_DIR (without) (:879-885,1535-1536).
 
 Deviation, on purpose: the shipped reference stops at a debug `print(...); exit()` (:1528) right
 after the first valid instance; this implements the evidently intended continuation.  The OBB
-comes from open3d in the reference (absent from its tree): yaw parity is UNPINNED.
+comes from open3d in the reference (absent from its tree); `cm3d_hull_obb` follows open3d 0.15's
+published algorithm (PCA of the convex-hull vertices) and is graded against the reference's own
+`get_depth_bbox` executed over a Qhull-based stand-in.
 """
 from __future__ import annotations
 
@@ -72,12 +74,17 @@ class kitti_object:
         return Calibration(os.path.join(self.calib_dir, "%06d.txt" % idx))
 
 
-def save_pred(pred_path, object_type, ltrb, wlh, xyz, yaw, conf, truncation=-1, occlusion=-1, alpha=-10):
-    """One KITTI label line, appended (kitti/2d_to_3d.py:879-885)."""
+def label_line(object_type, ltrb, wlh, xyz, yaw, conf, truncation=-1, occlusion=-1, alpha=-10) -> str:
+    """One KITTI label line (kitti/2d_to_3d.py:879-885)."""
     line = (f"{object_type} {truncation} {occlusion} {alpha} {ltrb[0]} {ltrb[1]} {ltrb[2]} {ltrb[3]} "
             f"{wlh[0]} {wlh[1]} {wlh[2]} {xyz[0]} {xyz[1]} {xyz[2]} {yaw}")
+    return line + ("\n" if conf is None else f" {conf}\n")
+
+
+def save_pred(pred_path, object_type, ltrb, wlh, xyz, yaw, conf, truncation=-1, occlusion=-1, alpha=-10):
+    """The reference's writer: one line appended per call (kitti/2d_to_3d.py:879-885)."""
     with open(pred_path, "a") as f:
-        f.write(line + ("\n" if conf is None else f" {conf}\n"))
+        f.write(label_line(object_type, ltrb, wlh, xyz, yaw, conf, truncation, occlusion, alpha))
 
 
 def frame_spec(kitti, frame_num: int, masks, data, cfg) -> FrameSpec:
@@ -94,7 +101,7 @@ def write_frame_labels(frame_num: int, data: dict, r, cfg, shape_priors: dict) -
     """Label lines of one frame from its LiftResult; returns the number of objects written."""
     pred_path = os.path.join(cfg.PRED_DIR, f"{frame_num:06}.txt")
     pseudo_path = os.path.join(cfg.PSEUDO_DIR, f"{frame_num:06}.txt")
-    n = 0
+    pred, pseudo = [], []
     for i, (label, score) in enumerate(zip(data["labels"], data["detection_scores"])):
         if r.counts[i] == 0 or r.counts[i] <= 3:                        # :1380, :1479-1480
             continue
@@ -106,10 +113,14 @@ def write_frame_labels(frame_num: int, data: dict, r, cfg, shape_priors: dict) -
         wlh = B.get_shape_prior(shape_priors, label)                    # raw label, like :1530
         wlh = [wlh[2], wlh[0], wlh[1]]
         center = [center[0], center[1] + wlh[0] / 2, center[2]]
-        save_pred(pred_path, detection_name, [0, 0, 0, 0], wlh, center, yaw, score)
-        save_pred(pseudo_path, detection_name, [0, 0, 0, 0], wlh, center, yaw, None)
-        n += 1
-    return n
+        pred.append(label_line(detection_name, [0, 0, 0, 0], wlh, center, yaw, score))
+        pseudo.append(label_line(detection_name, [0, 0, 0, 0], wlh, center, yaw, None))
+    # the reference appends line by line to the files it truncated when it read the frame; one write per file here
+    for path, lines in ((pred_path, pred), (pseudo_path, pseudo)):
+        if lines:
+            with open(path, "a") as f:
+                f.write("".join(lines))
+    return len(pred)
 
 
 def run(cfg, kitti=None, frame_range=None, lifter=None) -> int:
@@ -126,7 +137,8 @@ def run(cfg, kitti=None, frame_range=None, lifter=None) -> int:
     os.makedirs(cfg.PRED_DIR, exist_ok=True)
     os.makedirs(cfg.PSEUDO_DIR, exist_ok=True)
     todo = [f for f in (frame_range if frame_range is not None else range(len(kitti))) if f % world == rank]
-    pending = []
+    from collections import deque
+    pending = deque()
 
     def build(frame_num):
         t0 = time.time()
@@ -147,7 +159,7 @@ def run(cfg, kitti=None, frame_range=None, lifter=None) -> int:
     written = 0
     for res_batch in lifter.lift_frame_stream(frames(), batch_frames=cfg.batch_frames, timer=timer):
         for r in res_batch:
-            frame_num, data = pending.pop(0)
+            frame_num, data = pending.popleft()
             written += write_frame_labels(frame_num, data, r, cfg, shape_priors)
     timer["total"] += time.time() - total_start
     for operation in timer:

@@ -41,6 +41,7 @@ ratio = 0.8366
 SPLIT = "training"
 NUM_SAMPLES = None            # None = the reference's hard-coded 7481 (training) / 7518 (testing)
 BATCH_FRAMES = 64
+READER_THREADS = 8            # threads that read scans / masks ahead of the GPU (not in the reference)
 
 
 def main(kitti=None, frame_range=None, lifter=None):
@@ -50,7 +51,7 @@ def main(kitti=None, frame_range=None, lifter=None):
     cfg = stage.make_cfg(INPUT_PATH=INPUT_PATH, OUTPUT_DIR=OUTPUT_DIR, PRED_DIR=PRED_DIR, PSEUDO_DIR=PSEUDO_DIR,
                          INPUT_DIR=INPUT_DIR, KITTI_CLASS_MAPS=KITTI_CLASS_MAPS, DEVICE=DEVICE, min_dist=min_dist,
                          floor_thresh=floor_thresh, ratio=ratio, split=SPLIT, num_samples=NUM_SAMPLES,
-                         batch_frames=BATCH_FRAMES,
+                         batch_frames=BATCH_FRAMES, reader_threads=READER_THREADS,
                          shape_priors_path=os.path.join(os.path.dirname(os.path.abspath(__file__)), "cfg",
                                                         "shape_priors_chatgpt.json"))
     return stage.run(cfg, kitti, frame_range, lifter=lifter)

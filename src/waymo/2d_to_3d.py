@@ -39,6 +39,7 @@ ratio = 1024 / 1920
 SCENE_SLICE = (680, 710)      # scene_list[680:710]
 OUTPUT_FILE = "../../outputs/waymo/pred_0307_detic_train_680_710.bin"
 BATCH_FRAMES = 32
+READER_THREADS = 8            # threads that read scans / masks ahead of the GPU (not in the reference)
 
 
 def _tfrecord_scenes(scene_names):
@@ -60,7 +61,7 @@ def main(scenes=None, points_fn=None, lifter=None):
         raise RuntimeError("cm3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     cfg = stage.make_cfg(INPUT_PATH=INPUT_PATH, OUTPUT_DIR=OUTPUT_DIR, INPUT_DIR=INPUT_DIR, ATTRIBUTE_NAMES=ATTRIBUTE_NAMES,
                          DEVICE=DEVICE, CAM_LIST=CAM_LIST, min_dist=min_dist, floor_thresh=floor_thresh, ratio=ratio,
-                         scene_slice=SCENE_SLICE, output_path=OUTPUT_FILE, batch_frames=BATCH_FRAMES,
+                         scene_slice=SCENE_SLICE, output_path=OUTPUT_FILE, batch_frames=BATCH_FRAMES, reader_threads=READER_THREADS,
                          shape_priors_path=os.path.join(os.path.dirname(os.path.abspath(__file__)), "cfg",
                                                         "shape_priors_chatgpt.json"))
     if scenes is None:

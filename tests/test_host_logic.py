@@ -381,3 +381,45 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["config"]["workload"].startswith("C1:")
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_vectorised_waymo_pass2_equals_the_per_object_path():
+    """`waymo_stage.centroids_to_global` / `frame_objects` (one numpy pass per frame) against the per-instance
+    functions that call torch / scipy exactly where the reference does (waymo:684-699, 803-858): the global
+    centroids bit for bit, the objects within 1e-10 (a batched fp64 matrix product may order its terms
+    differently)."""
+    import json
+    from types import SimpleNamespace as NS
+    from scipy.spatial.transform import Rotation as R
+    from cm3d_b200 import boxes as B
+    from cm3d_b200 import waymo_stage as W
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sp = json.load(open(os.path.join(root, "src", "waymo", "cfg", "shape_priors_chatgpt.json")))
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        pose = np.eye(4)
+        pose[:3, :3] = R.from_euler("xyz", [0.01 * trial, -0.02, rng.uniform(-3, 3)]).as_matrix()
+        pose[:3, 3] = [512.3 + 1000 * trial, -811.7, 12.5]
+        frame = NS(pose=NS(transform=[float(v) for v in pose.reshape(-1)]), context=NS(name="seg"), timestamp_micros=123456 + trial)
+        k = 300
+        labs = [l for l in B.NUSC_TO_WAYMO if B.NUSC_TO_WAYMO[l]] + ["human"]
+        labels = [labs[i] for i in rng.integers(0, len(labs), k)]
+        local = np.column_stack([rng.normal(0, 30, k), rng.normal(0, 30, k), rng.normal(0, 1, k)]).astype(np.float32)
+        local[3], local[4], local[5] = [0, 0, 0], [5, 0, 1], [0, -7, 1]
+        cg = W.centroids_to_global(local, frame)
+        one = np.array([W.centroid_to_global(c, frame) for c in local])
+        assert np.array_equal(cg.view(np.uint32), one.view(np.uint32))
+        yaw = rng.uniform(-np.pi, np.pi, k).astype(np.float32)
+        scores = rng.random(k)
+        got = W.frame_objects(frame, labels, scores, cg, yaw, sp)
+        want = [W.object_of(frame, labels[i], scores[i], cg[i], yaw[i], sp) for i in range(k)]
+        for a, b in zip(got, want):
+            assert set(a) == set(b)
+            for key in a:
+                if isinstance(a[key], float):
+                    assert (np.isnan(a[key]) and np.isnan(b[key])) or abs(a[key] - b[key]) <= 1e-10, key
+                else:
+                    assert a[key] == b[key], key
+    assert W.frame_objects(frame, [], [], np.zeros((0, 3)), np.zeros(0, np.float32), sp) == []
+    with pytest.raises(ValueError):
+        W.frame_objects(frame, ["barrier"], [0.5], cg[:1], yaw[:1], sp)
