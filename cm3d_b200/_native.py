@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CM3D_B200_LIB") or os.path.join(_HERE, "_lib", "libcm3d_b200.so")   # env: kernel experiments
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -38,10 +38,28 @@ PROTOTYPES = {
     "cm3d_nearest_lane": [_P, _I, _P, _I, _P, _P, _P],
     "cm3d_selftest_sqrt": [_P, _P],
     "cm3d_selftest_sqrt_approx": [_P, _P],
+    "cm3d_lift_batch": [_P],
     "cm3d_pack_plan": [_P, _P],
     "cm3d_pack_fill": [_P, _P, _P, _P, _P, _P, _P, _P],
 }
 EXPORTS = ["cm3d_abi_version", "cm3d_error_string", "cm3d_hull_obb_ws_words"] + list(PROTOTYPES)
+
+
+
+class BatchArgs(ctypes.Structure):
+    """`cm3d_batch_args` of include/cm3d_b200.h (field for field)."""
+    _fields_ = ([(n, ctypes.c_int32) for n in ("n_frames", "n_inst", "n_tiles", "n_vcams", "max_cells", "max_words", "max_runs",
+                                               "max_inst_per_frame", "masks_kind", "want_obb", "obb_mode", "obb_min_pts",
+                                               "screen_min_pts", "screen_flags", "max_items", "reserved")] +
+                [(n, ctypes.c_int64) for n in ("bits_words", "seg_cap", "hull_ws_words", "out_words", "mask_bytes")] +
+                [(n, ctypes.c_void_p) for n in (
+                    "raw", "tile_sweep", "sweep_desc", "frame_desc", "vcam_desc", "cam_inst_list", "inst_desc", "chains", "mask",
+                    "mask_off", "out", "frame_n", "seg_off", "item_off", "medoid_local", "medoid_point_idx", "centroid", "errflags",
+                    "runs", "run_start", "row_range", "bits_raw", "bits", "bbox", "vcam_grid", "xyzw", "tile_cnt", "tile_prefix",
+                    "hits", "tile_inst_cnt", "tile_inst_base", "medoid_best", "item_inst", "seg_point_idx", "seg_xyzw",
+                    "screen_sums", "screen_min", "sym_ws", "screen_stats", "item_info", "obb", "hull_info", "hull_ws", "stream",
+                    "stream_medoid", "launches")])
+
 
 _lib = None
 

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT_DIR = os.path.join(_HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "libcm3d_b200.so")
-SOURCES = ["masks.cu", "lift.cu", "medoid.cu", "obb.cu", "boxes.cu", "extras.cu", "pack.cu"]
+SOURCES = ["masks.cu", "lift.cu", "medoid.cu", "obb.cu", "boxes.cu", "extras.cu", "pack.cu", "batch.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false", "-shared", "-Xcompiler", "-fPIC"]
 

@@ -209,6 +209,8 @@ class Lifter:
         self.timing = None          # dict label -> [(start_event, end_event)] when bench.py profiles
         self.obb_mode = 0           # KITTI box: 0 = hull vertices (open3d's algorithm), 1 = all member points (diagnostics)
         self.last_hull_info = None  # device int32[I]: hull vertex count per instance (-1: flat cloud -> the reference's fallback box)
+        self.fused = True           # run(): one C call over one workspace (cm3d_lift_batch) when nothing asks for the call-by-call path
+        self._launch_count = ctypes.c_int32(0)
 
     def _buf(self, n, dtype=torch.int32):
         """Uninitialised device buffer of n elements, from an allocation of a rounded-up size class."""
@@ -277,6 +279,9 @@ class Lifter:
         `box_search=n_angles` adds the orientation / extent search (LiftResult.box)."""
         denoise = denoise if denoise is not None else self.denoise
         box_search = box_search if box_search is not None else self.box_search
+        if (self.fused and self.timing is None and do_medoid and not want_pix and not want_col_sums and denoise is None
+                and not box_search):
+            return self._run_fused(db, seg_cap, want_obb, overlap)
         pb, dev = db.pb, self.device
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         F, I, T = pb.n_frames, pb.n_inst, pb.n_tiles
@@ -435,6 +440,89 @@ class Lifter:
             xyzw, tile_cnt, tile_prefix, pix, hits, bits, bbox, seg_off_raw, obb
         return do
 
+    _MASK_KIND = {"dense": 0, "rle": 1, "rle_str": 2}
+
+    def _run_fused(self, db: DeviceBatch, seg_cap, want_obb, overlap: bool) -> DeviceOutputs:
+        """run() as ONE C call (cm3d_lift_batch, csrc/batch.cu) over ONE workspace allocation: the same entry points in
+        the same order with the same arguments, minus ~15 foreign-function calls and ~30 allocations per batch."""
+        pb, dev = db.pb, self.device
+        F, I, T = pb.n_frames, pb.n_inst, pb.n_tiles
+        n_slots = max(T, 1) * TILE
+        if seg_cap is None:
+            factor = self.seg_factor if self._seg_ratio is None else min(self.seg_factor, 1.5 * self._seg_ratio + 0.05)
+            seg_cap = int(factor * pb.n_raw_points) + 1024
+        seg_cap = _round_up((int(seg_cap) + 3) & ~3) if overlap else (int(seg_cap) + 3) & ~3
+        lay = self._out_layout(F, I)
+        kind = self._MASK_KIND[pb.masks_kind]
+        if want_obb is None:
+            want_obb = pb.any_kitti
+        want_obb = bool(want_obb and I)
+        screen = self.screen_min_pts > 0
+        sym = screen and not (self.screen_flags & 3)
+        max_items = seg_cap // MEDOID_COLS + 2 * I
+        hull_words = int(N.load().cm3d_hull_obb_ws_words(seg_cap)) if (want_obb and self.obb_mode == 0) else 1
+        mask_n = int(db.mask.numel())
+        I1 = max(I, 1)
+        sizes = (("out", 4 * lay["_words"]), ("runs", 4 * mask_n if kind == 2 else 0), ("run_start", 4 * mask_n if kind else 0),
+                 ("row_range", 8 * I1), ("bits_raw", 4 * max(pb.bits_words, 1)), ("bits", 4 * max(pb.bits_words, 1)),
+                 ("bbox", 16 * I1), ("vcam_grid", 4 * max(pb.grid_words, 1)), ("xyzw", 16 * n_slots), ("tile_cnt", 4 * max(T, 1)),
+                 ("tile_prefix", 4 * max(T, 1)), ("hits", 4 * n_slots), ("tile_inst_cnt", 2 * max(pb.cnt_total, 1)),
+                 ("tile_inst_base", 4 * max(pb.cnt_total, 1)), ("medoid_best", 8 * I1), ("item_inst", 4 * I1),
+                 ("seg_point_idx", 4 * seg_cap), ("seg_xyzw", 16 * seg_cap), ("screen_sums", 4 * seg_cap if screen else 0),
+                 ("screen_min", 20 * I1 if screen else 0), ("sym_ws", 20 * seg_cap if sym else 0), ("screen_stats", 4 if screen else 0),
+                 ("item_info", 16 * max(max_items, 1)), ("obb", 64 * I1 if want_obb else 0), ("hull_info", 4 * I1 if want_obb else 0),
+                 ("hull_ws", 4 * hull_words if want_obb else 0))
+        off, pos = {}, 0
+        for name, nbytes in sizes:
+            off[name] = (pos, nbytes)
+            pos += (nbytes + 255) & ~255
+        ws = torch.empty(_round_up(max(pos, 256)), dtype=torch.uint8, device=dev)
+        base = ws.data_ptr()
+
+        def view(name, dtype):
+            a, n = off[name]
+            return ws[a:a + n].view(dtype) if n else None
+
+        front = torch.cuda.current_stream(dev)
+        phase2 = None
+        if overlap:
+            if self._med_stream is None:
+                self._med_stream = torch.cuda.Stream(dev)
+            phase2 = self._med_stream
+            ws.record_stream(phase2)
+        a = N.BatchArgs()
+        a.n_frames, a.n_inst, a.n_tiles, a.n_vcams = F, I, T, pb.n_vcams
+        a.max_cells, a.max_words, a.max_runs, a.max_inst_per_frame = pb.max_cells, pb.max_words, pb.max_runs, pb.max_inst_per_frame
+        a.masks_kind, a.want_obb, a.obb_mode, a.obb_min_pts = kind, int(want_obb), int(self.obb_mode), 4
+        a.screen_min_pts, a.screen_flags, a.max_items = (int(self.screen_min_pts) if screen else 0), int(self.screen_flags), max_items
+        a.bits_words, a.seg_cap, a.hull_ws_words, a.out_words, a.mask_bytes = max(pb.bits_words, 1), seg_cap, hull_words, lay["_words"], mask_n
+        a.raw, a.mask, a.mask_off = db.raw.data_ptr(), db.mask.data_ptr(), db.mask_off.data_ptr()
+        meta = db.meta.data_ptr()
+        for name in ("tile_sweep", "sweep_desc", "frame_desc", "vcam_desc", "cam_inst_list", "inst_desc", "chains"):
+            setattr(a, name, meta + 4 * pb.off[name])
+        out_base = base + off["out"][0]
+        for name in ("frame_n", "seg_off", "item_off", "medoid_local", "medoid_point_idx", "centroid", "errflags"):
+            setattr(a, name, out_base + 4 * lay[name][0])
+        for name, (p0, nbytes) in off.items():
+            setattr(a, name, base + p0 if nbytes else None)
+        a.stream = front.cuda_stream
+        a.stream_medoid = phase2.cuda_stream if phase2 is not None else None
+        a.launches = ctypes.addressof(self._launch_count)
+        N.call("cm3d_lift_batch", ctypes.byref(a))
+        self.launches += self._launch_count.value
+        do = DeviceOutputs(db, view("out", torch.int32), lay, seg_cap, view("seg_point_idx", torch.int32), view("seg_xyzw", torch.float32),
+                           view("xyzw", torch.float32), view("tile_cnt", torch.int32), view("tile_prefix", torch.int32))
+        do.hits, do.bits, do.bbox = view("hits", torch.int32), view("bits", torch.int32), view("bbox", torch.int32)
+        do.obb = view("obb", torch.float32)
+        if phase2 is not None:
+            do.done = torch.cuda.Event()
+            do.done.record(phase2)
+        self.last_hull_info = view("hull_info", torch.int32)
+        self.last_screen_stats = view("screen_stats", torch.int32)
+        smin = view("screen_min", torch.int32)
+        self.last_screen_modes = smin[I:4 * I] if (I and smin is not None) else None
+        return do
+
     def _run_phase2(self, db, out, lay, seg_cap, seg_point_idx, seg_xyzw, medoid_best, item_inst, st,
                     want_col_sums, do_medoid, box_search) -> DeviceOutputs:
         pb, dev = db.pb, self.device
@@ -467,7 +555,8 @@ class Lifter:
                    _ptr(screen_stats), _ptr(item_pos),
                    _ptr(op("medoid_local")), _ptr(op("medoid_point_idx")), _ptr(op("centroid")), _ptr(op("errflags")), st)
             # expand_items, k_medoid, finalize; + classify, screen, verify; + screen_sym, screen_min; + permute
-            self.launches += (6 if self.screen_flags & 1 else (8 if self.screen_flags & 2 else 9)) if screen else 3
+            self.launches += ((6 if self.screen_flags & 1 else (8 if self.screen_flags & 2 or sym_ws is None else 9)) +
+                              (1 if sym_ws is not None and not self.screen_flags & 4 else 0)) if screen else 3   # + prune
         self.last_screen_stats = screen_stats
         self.last_screen_modes = screen_min[I:4 * I] if (do_medoid and I and screen_min is not None) else None
         box = None

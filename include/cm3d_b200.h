@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define CM3D_ABI_VERSION 12
+#define CM3D_ABI_VERSION 13
 #define CM3D_TILE 1024          /* points per tile: compaction / count granule */
 #define CM3D_MAX_INST 254       /* instances per frame (hit ids are one byte, 0 = none, 255 = overflow) */
 #define CM3D_MAX_VCAMS 16       /* (camera, mask size) combinations per frame */
@@ -224,7 +224,8 @@ int cm3d_medoid(const float *seg_xyzw, int64_t seg_cap, const int32_t *seg_off,
  * else ceil(floor32(m)/CM3D_MEDOID_COLS) full items + one tail item when m % 32 != 0). */
 int cm3d_medoid_items(int m, int min_pts);
 
-/* ---- KITTI orientation (PARITY UNPINNED: open3d is not in the reference tree) ------------------ */
+/* ---- KITTI orientation (open3d is not in the reference tree: graded against the reference's get_depth_bbox run over a
+ * Qhull-based stand-in) ------------------------------------------------------------------------- */
 
 /* open3d's oriented bounding box of every instance with at least min_pts points and the reference's yaw
  * (src/kitti/2d_to_3d.py:855-876,1524): obb[16*i..] = yaw, centre xyz, wlh (after the reference's
@@ -290,6 +291,56 @@ int cm3d_selftest_sqrt(unsigned long long *mismatches, void *stream);
  * approximate square root (MUFU.SQRT) and IEEE sqrt.rn.f32 over 0 and [2^-101, FLT_MAX].  The
  * screen error bound assumes <= 4; the GPU suite pins <= 2. */
 int cm3d_selftest_sqrt_approx(unsigned *max_ulp, void *stream);
+
+/* ---- the whole launch sequence of one batch in ONE call ------------------------------------------------------ */
+
+/* What `Lifter.run` does call by call (masks -> grid -> aggregate -> project -> scan -> gather -> [hull boxes] -> medoid),
+ * for callers whose batches are short enough that ~15 foreign-function calls and ~30 allocations per batch show
+ * (one frame per call, Waymo's 16-frame batches).  Every pointer is device memory owned by the caller; sizes are
+ * those the individual entry points document.  The call zeroes `out` (out_words words: the label block that holds
+ * frame_n .. errflags, in any layout - only the field pointers are used) and bits_raw, then launches.
+ * stream_medoid: NULL or == stream -> everything on `stream`; otherwise the medoid runs on stream_medoid behind an
+ * event recorded after the gather (the hull boxes stay on `stream`, next to it) and stream_medoid finally waits for
+ * the boxes, so that "stream_medoid is done" means "the batch is done".  Optional (may be NULL): row_range with
+ * masks_kind 0, obb / hull_info / hull_ws when want_obb == 0, sym_ws, screen_stats (zeroed by the call), item_info,
+ * screen_sums / screen_min when screen_min_pts == 0.  *launches (optional) receives the number of kernels launched. */
+typedef struct cm3d_batch_args {
+    int32_t n_frames, n_inst, n_tiles, n_vcams, max_cells, max_words, max_runs, max_inst_per_frame;
+    int32_t masks_kind;                 /* 0 dense uint8 masks, 1 COCO run lengths, 2 COCO `counts` strings */
+    int32_t want_obb, obb_mode, obb_min_pts;
+    int32_t screen_min_pts, screen_flags, max_items, reserved;
+    int64_t bits_words, seg_cap, hull_ws_words, out_words, mask_bytes;
+    const float *raw;
+    const int32_t *tile_sweep, *sweep_desc, *frame_desc, *vcam_desc, *cam_inst_list, *inst_desc;
+    const uint32_t *chains;
+    const uint8_t *mask;
+    const int64_t *mask_off;
+    int32_t *out, *frame_n, *seg_off, *item_off, *medoid_local, *medoid_point_idx;
+    float *centroid;
+    int32_t *errflags;
+    uint32_t *runs, *run_start;
+    int32_t *row_range;
+    uint32_t *bits_raw, *bits;
+    int32_t *bbox;
+    uint32_t *vcam_grid;
+    float *xyzw;
+    int32_t *tile_cnt, *tile_prefix;
+    uint32_t *hits;
+    uint16_t *tile_inst_cnt;
+    int32_t *tile_inst_base;
+    unsigned long long *medoid_best;
+    int32_t *item_inst, *seg_point_idx;
+    float *seg_xyzw, *screen_sums;
+    uint32_t *screen_min;
+    float *sym_ws;
+    int32_t *screen_stats, *item_info;
+    float *obb;
+    int32_t *hull_info, *hull_ws;
+    void *stream, *stream_medoid;
+    int32_t *launches;                  /* host pointer */
+} cm3d_batch_args;
+
+int cm3d_lift_batch(const cm3d_batch_args *a);
 
 /* ---- host-side packer (no CUDA call inside; releases nothing, allocates nothing the caller sees) ---------- */
 

@@ -813,6 +813,47 @@ def test_cuda_graph_path_equals_plain_path(lifter):
     assert 2 <= g.captures <= len(frames)
 
 
+def test_one_call_launch_sequence_equals_call_by_call(lifter):
+    """`cm3d_lift_batch` (Lifter.run's default: the whole launch sequence behind one C call over one workspace)
+    against the call-by-call sequence on nuScenes-, KITTI- and Waymo-shaped batches, dense / run-length / counts-string
+    masks, one stream and two: label block, member index lists, gathered points, eroded-mask boxes and hull boxes,
+    byte for byte; the launch counters agree."""
+    import torch
+    from cm3d_b200 import synthetic as S
+    batches = []
+    for cfg, kinds in (("c2", "str"), ("c3", "str"), ("c4", "rle"), ("c1", "dense")):
+        fr = []
+        for i in range(3):
+            f = S.make_frame(cfg, 20 + i, scale=0.3, dense_masks=(kinds == "dense"))
+            if kinds == "str":
+                f.masks = S.compress_rles(f.masks)
+            fr.append(f)
+        batches.append(fr)
+    for fr in batches:
+        db = lifter.upload(lifter.pack(fr))
+        for overlap in (False, True):
+            got = {}
+            for fused in (True, False):
+                lifter.fused = fused
+                n0 = lifter.launches
+                do = lifter.run(db, overlap=overlap)
+                if overlap:
+                    do.done.synchronize()
+                torch.cuda.synchronize()
+                total = int(do.out[do.layout["seg_off"][0] + db.pb.n_inst].item())
+                got[fused] = (do.out.cpu().numpy().copy(), do.seg_point_idx[:total].cpu().numpy().copy(),
+                              do.seg_xyzw.view(4, -1)[:3, :total].cpu().numpy().copy(), do.bbox[:4 * db.pb.n_inst].cpu().numpy().copy(),
+                              None if do.obb is None else do.obb.cpu().numpy().copy(), lifter.launches - n0)
+            lifter.fused = True
+            a, b = got[True], got[False]
+            assert a[5] == b[5] and a[5] > 10
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            assert np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32)) and np.array_equal(a[3], b[3])
+            assert (a[4] is None) == (b[4] is None)
+            if a[4] is not None:
+                assert np.array_equal(a[4].view(np.uint32), b[4].view(np.uint32))
+
+
 def test_c5_seeds_stream_against_c_oracle(lifter):
     """The bench's own frames (config C5: seeds 5,000,000 + i, masks as counts strings, xyz-only on the wire)
     through the streaming entry the drop-in scripts use, against the C oracle: member counts, medoid
