@@ -6,10 +6,10 @@ P=${1:-r02c}
 O=gpurun_out
 set -x
 timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6 > $O/${P}_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/${P}_smoke.log 2>&1
 timeout 700 python bench.py --steps 20 --warmup 5 > $O/${P}_c2.json 2> $O/${P}_c2.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/${P}_ref.json 2> $O/${P}_ref.err
 for c in c1 c3 c4; do timeout 600 python bench.py --config $c --steps 20 --warmup 5 > $O/${P}_$c.json 2> $O/${P}_$c.err; done
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-framespec-leg --no-latency-leg --reader-threads 4 > $O/${P}_disk4.json 2> $O/${P}_disk4.err
 LEGS="--no-cpu-baseline --no-framespec-leg --no-disk-leg --no-latency-leg"
 CMD="python bench.py --steps 2 --warmup 3 $LEGS --stream-frames 128 --e2e-ramp 0"
 $CMD > $O/${P}_plain.log 2>&1 &&
