@@ -129,9 +129,9 @@ def erode_to_wh_bool(maskarr):
 def _apply_ops(pc, ops):
     for kind, m in ops:
         if kind == "R":
-            pc.rotate(torch.from_numpy(m).to(dtype=torch.float32))
+            pc.rotate(torch.from_numpy(np.array(m)).to(dtype=torch.float32))
         elif kind == "T":
-            pc.translate(torch.from_numpy(m).to(dtype=torch.float32))
+            pc.translate(torch.from_numpy(np.array(m)).to(dtype=torch.float32))
         else:
             raise ValueError("column-major clouds only take R/T ops")
 
