@@ -414,7 +414,6 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     lifter.timing = None
-    lifter.launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     overlap = not args.no_overlap
     cur = torch.cuda.current_stream(dev)
@@ -422,7 +421,7 @@ def run_ours(args, rank, world, local_rank):
     # the medoid (XU-bound) on the lifter's second stream, so step k+1's front end runs next to step k's medoid
     front = torch.cuda.Stream(dev, priority=-1) if overlap else cur
     import collections
-    # the last eight steps' buffers stay referenced (as in the streaming path's pipeline): a workspace that is
+    # the last few steps' buffers (--ring) stay referenced (as in the streaming path's pipeline): a workspace that is
     # freed while the other stream still uses it cannot be reused, and the allocator would cudaMalloc a new one
     ring = collections.deque(maxlen=max(1, args.ring) if overlap else 1)
     # warm-up: every resident batch at least once in the timed configuration (their workspace sizes differ, and the
@@ -431,13 +430,14 @@ def run_ours(args, rank, world, local_rank):
         with torch.cuda.stream(front):
             ring.append(lifter.run(dbs[w % n_res], seg_cap=seg_cap, overlap=overlap))
     barrier()
+    lifter.launches = 0                     # counts the timed region only
     e0.record(cur)
     front.wait_stream(cur)
     t_host = time.perf_counter()
     with torch.cuda.stream(front):
         for k in range(args.steps):
             if overlap and len(ring) == ring.maxlen:
-                ring[0].done.synchronize()      # the host stays at most eight steps ahead (the GPU always has work queued):
+                ring[0].done.synchronize()      # the host stays at most `ring` steps ahead (the GPU always has work queued):
                 #                                 buffers are then freed AFTER their last use and recycled without cudaMalloc
             ring.append(lifter.run(dbs[k % n_res], seg_cap=seg_cap, overlap=overlap))
     t_host = (time.perf_counter() - t_host) / args.steps * 1e3
