@@ -781,7 +781,7 @@ def main():
                     "32 measured 2.8 %% slower on one GPU: two launch sequences per step have two medoid tails)")
     ap.add_argument("--e2e-ramp", type=int, default=16, help="frames per piece of the FIRST step of the end-to-end leg (0 = no ramp-up)")
     ap.add_argument("--pack-workers", type=int, default=0)
-    ap.add_argument("--stream-batch", type=int, default=32, help="frames per launch sequence of the FrameSpec stream leg")
+    ap.add_argument("--stream-batch", type=int, default=40, help="frames per launch sequence of the FrameSpec stream leg")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-frames", type=int, default=2, help="frames of the CPU sample")
     ap.add_argument("--workers", type=int, default=0)
