@@ -42,7 +42,7 @@ PROTOTYPES = {
     "cm3d_pack_plan": [_P, _P],
     "cm3d_pack_fill": [_P, _P, _P, _P, _P, _P, _P, _P],
 }
-EXPORTS = ["cm3d_abi_version", "cm3d_error_string", "cm3d_hull_obb_ws_words"] + list(PROTOTYPES)
+EXPORTS = ["cm3d_abi_version", "cm3d_error_string", "cm3d_hull_obb_ws_words", "cm3d_batch_args_size"] + list(PROTOTYPES)
 
 
 
@@ -86,6 +86,10 @@ def load():
     v = lib.cm3d_abi_version()
     if v != ABI_VERSION:
         raise Cm3dError(f"libcm3d_b200.so has ABI {v}, python side expects {ABI_VERSION}: rebuild")
+    lib.cm3d_batch_args_size.restype = ctypes.c_int
+    if lib.cm3d_batch_args_size() != ctypes.sizeof(BatchArgs):
+        raise Cm3dError(f"cm3d_batch_args is {lib.cm3d_batch_args_size()} bytes in the library, {ctypes.sizeof(BatchArgs)} in "
+                        "cm3d_b200/_native.py: BatchArgs - the two declarations have drifted apart")
     # Kernel launches return in microseconds: they are bound through PyDLL, which keeps the GIL, so the launching
     # thread does not queue behind the packer threads' Python sections a dozen times per batch.  The host packer
     # (cm3d_pack_*: milliseconds of memcpy) stays on CDLL, which releases it.

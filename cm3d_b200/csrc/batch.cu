@@ -20,6 +20,8 @@
         if (e__ != cudaSuccess) return -(1000 + (int)e__);       \
     } while (0)
 
+extern "C" int cm3d_batch_args_size(void) { return (int)sizeof(cm3d_batch_args); }
+
 extern "C" int cm3d_lift_batch(const cm3d_batch_args *a)
 {
     if (!a) return CM3D_EINVAL;

@@ -341,6 +341,8 @@ typedef struct cm3d_batch_args {
 } cm3d_batch_args;
 
 int cm3d_lift_batch(const cm3d_batch_args *a);
+/* sizeof(cm3d_batch_args) as this library was compiled: a binding checks its own mirror of the struct against it. */
+int cm3d_batch_args_size(void);
 
 /* ---- host-side packer (no CUDA call inside; releases nothing, allocates nothing the caller sees) ---------- */
 

@@ -74,3 +74,13 @@ def test_sass_is_sm100a_with_bulk_copy_and_packed_fma(lib_path):
     assert "sm_100a" in out
     assert "UBLKCP" in out
     assert "FFMA2" in out
+
+
+def test_batch_args_mirror_and_null_call(lib_path):
+    """The ctypes mirror of `cm3d_batch_args` has the library's size (checked at load, and here), and the one-call
+    entry point rejects a null argument block before it touches CUDA."""
+    import ctypes
+    from cm3d_b200 import _native as N
+    lib = N.load()
+    assert lib.cm3d_batch_args_size() == ctypes.sizeof(N.BatchArgs)
+    assert lib.cm3d_lift_batch(None) == -1          # CM3D_EINVAL
