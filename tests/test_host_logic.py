@@ -423,3 +423,33 @@ def test_vectorised_waymo_pass2_equals_the_per_object_path():
     assert W.frame_objects(frame, [], [], np.zeros((0, 3)), np.zeros(0, np.float32), sp) == []
     with pytest.raises(ValueError):
         W.frame_objects(frame, ["barrier"], [0.5], cg[:1], yaw[:1], sp)
+
+
+def test_prefetch_map_keeps_order_bounds_lookahead_and_raises_in_place():
+    """`lifter.prefetch_map` (the stages' reader threads): results in input order whatever the completion order, the
+    input iterator is never drained further than the look-ahead, and an exception surfaces at its item's position."""
+    import threading
+    import time
+    torch = pytest.importorskip("torch")
+    from cm3d_b200.lifter import prefetch_map
+    pulled = []
+
+    def items():
+        for k in range(40):
+            pulled.append(k)
+            yield k
+
+    def work(k):
+        time.sleep(0.002 * ((k * 7) % 5))
+        if k == 25:
+            raise KeyError("frame 25")
+        return k * k
+
+    got = []
+    with pytest.raises(KeyError):
+        for v in prefetch_map(work, items(), workers=4):
+            got.append(v)
+            assert len(pulled) <= len(got) + 2 * 4 + 1
+    assert got == [k * k for k in range(25)]
+    assert list(prefetch_map(lambda k: k + 1, range(5), workers=1)) == [1, 2, 3, 4, 5]
+    assert list(prefetch_map(lambda k: threading.get_ident(), range(3), workers=1)) == [threading.get_ident()] * 3
