@@ -42,7 +42,7 @@ PROTOTYPES = {
     "cm3d_pack_plan": [_P, _P],
     "cm3d_pack_fill": [_P, _P, _P, _P, _P, _P, _P, _P],
 }
-EXPORTS = ["cm3d_abi_version", "cm3d_error_string", "cm3d_hull_obb_ws_words", "cm3d_batch_args_size"] + list(PROTOTYPES)
+EXPORTS = ["cm3d_abi_version", "cm3d_error_string", "cm3d_hull_obb_ws_words", "cm3d_batch_args_size", "cm3d_pack_input_size"] + list(PROTOTYPES)
 
 
 

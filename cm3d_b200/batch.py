@@ -563,6 +563,9 @@ def pack_frames_native(frames: Sequence[FrameSpec], pin: bool = False, pool: "Pi
     global _PackInput
     if _PackInput is None:
         _PackInput = _pack_input_type()
+        lib.cm3d_pack_input_size.restype = ctypes.c_int
+        if lib.cm3d_pack_input_size() != ctypes.sizeof(_PackInput):
+            raise N.Cm3dError("cm3d_pack_input: the library's struct and batch.py's mirror have drifted apart")
     inp = _PackInput(F, len(sw_ptr), int(cam_K.size), n_inst)
     for k, a in arrs.items():
         setattr(inp, k, _ptr_of(a))

@@ -215,6 +215,8 @@ int cull_planes(const OpRef *ops, int n_ops, const float *K32, int W, int H, flo
 
 extern "C" {
 
+int cm3d_pack_input_size(void) { return (int)sizeof(cm3d_pack_input); }
+
 // plan[]: 0 n_tiles, 1 n_vcams, 2 n_chains, 3 raw floats (incl. 4 of padding), 4 meta words, 5 mask bytes,
 // 6..12 word offsets of tile_sweep, sweep_desc, frame_desc, vcam_desc, cam_inst_list, inst_desc, chains in meta,
 // 13 max_inst_per_frame, 14 n_raw_points.  Returns 0, or CM3D_ELIMIT / CM3D_EINVAL.

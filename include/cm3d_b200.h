@@ -367,6 +367,8 @@ typedef struct cm3d_pack_input {
  * tile_sweep, sweep_desc, frame_desc, vcam_desc, cam_inst_list, inst_desc, chains in meta, 13 max instances per
  * frame, 14 raw points.  CM3D_ELIMIT when a frame exceeds CM3D_MAX_INST / CM3D_MAX_VCAMS. */
 int cm3d_pack_plan(const cm3d_pack_input *in, int64_t *plan);
+/* sizeof(cm3d_pack_input) as compiled (for a binding's own mirror of the struct). */
+int cm3d_pack_input_size(void);
 
 /* Fills raw (plan[3] floats), meta (plan[4] words), mask (plan[5] bytes: the counts strings), mask_off
  * (n_inst + 1), vcam_keys (plan[1] x {frame, camera, W, H}) and out[8] = cnt_total, bits_words, max_words,
