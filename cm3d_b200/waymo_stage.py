@@ -85,7 +85,22 @@ def _wxyz_of_matrix32(rot32):
     return (q[3], q[0], q[1], q[2])
 
 
+_CAM_SPECS = {}
+
+
 def cam_spec(cam_calib, ratio: float) -> CamSpec:
+    """Chain + scaled intrinsics of one camera.  A segment's calibration is the same in every frame (the reference
+    recomputes it per mask, waymo:557-593): kept by value."""
+    key = (tuple(cam_calib.extrinsic.transform), tuple(cam_calib.intrinsic), float(ratio))
+    spec = _CAM_SPECS.get(key)
+    if spec is None:
+        if len(_CAM_SPECS) > 4096:
+            _CAM_SPECS.clear()
+        spec = _CAM_SPECS[key] = _cam_spec(cam_calib, ratio)
+    return spec
+
+
+def _cam_spec(cam_calib, ratio: float) -> CamSpec:
     import torch
     axes = torch.Tensor([[0, -1, 0, 0], [0, 0, -1, 0], [1, 0, 0, 0], [0, 0, 0, 1]]).to(dtype=torch.float32)
     axes = torch.linalg.inv(axes)                                        # waymo:557-562
