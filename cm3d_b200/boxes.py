@@ -133,10 +133,16 @@ def circle_nms(dets: np.ndarray, det_labels: Sequence, threshs_by_label: dict) -
         idx = order[labels[order] == label]              # this class, best score first
         x, y, thr = dets[idx, 0], dets[idx, 1], threshs_by_label[label]
         live = np.ones(idx.size, dtype=bool)
-        for a in range(idx.size - 1):
-            if live[a]:
-                d = (x[a] - x[a + 1:]) ** 2 + (y[a] - y[a + 1:]) ** 2
-                live[a + 1:] &= ~(d <= thr)
+        if idx.size <= 1024:                             # all pairs of the class at once, then the greedy pass over rows
+            far = ~(((x[:, None] - x[None, :]) ** 2 + (y[:, None] - y[None, :]) ** 2) <= thr)
+            for a in range(idx.size - 1):
+                if live[a]:
+                    live[a + 1:] &= far[a, a + 1:]
+        else:
+            for a in range(idx.size - 1):
+                if live[a]:
+                    d = (x[a] - x[a + 1:]) ** 2 + (y[a] - y[a + 1:]) ** 2
+                    live[a + 1:] &= ~(d <= thr)
         alive[idx[~live]] = False
     keep = np.flatnonzero(alive)
     return [int(k) for k in keep[np.argsort(rank[keep])]]

@@ -46,11 +46,28 @@ def _ld(field: int, payload: bytes) -> bytes:
     return _key(field, 2) + _varint(len(payload)) + payload
 
 
+_BOX = struct.Struct("<" + "Bd" * 7)                         # seven (key, double) pairs: keys (n << 3) | 1
+_BOX_KEYS = tuple((n << 3) | 1 for _, n in _BOX_FIELDS)
+_TAILS = {}                                                   # per (context_name, timestamp) / per id: the constant bytes
+
+
 def encode_object(o: dict) -> bytes:
-    box = b"".join(_key(n, 1) + struct.pack("<d", float(o[name])) for name, n in _BOX_FIELDS)
-    label = _ld(1, box) + _key(3, 0) + _varint(int(o["type"])) + _ld(4, o.get("id", "unique object tracking ID").encode())
-    return (_ld(1, label) + _key(2, 5) + struct.pack("<f", float(o["score"])) + _ld(3, o["context_name"].encode()) +
-            _key(4, 0) + _varint(int(o["frame_timestamp_micros"])))
+    """One `Object` (field order and presence as `SerializeToString` of the proto2 message with every field set)."""
+    k = _BOX_KEYS
+    box = _BOX.pack(k[0], float(o["center_x"]), k[1], float(o["center_y"]), k[2], float(o["center_z"]), k[3], float(o["width"]),
+                    k[4], float(o["length"]), k[5], float(o["height"]), k[6], float(o["heading"]))
+    oid = o.get("id", "unique object tracking ID")
+    id_part = _TAILS.get(oid)
+    if id_part is None:
+        id_part = _TAILS[oid] = _ld(4, oid.encode())
+    label = b"\x0a" + _varint(len(box)) + box + b"\x18" + _varint(int(o["type"])) + id_part
+    ck = (o["context_name"], int(o["frame_timestamp_micros"]))
+    tail = _TAILS.get(ck)
+    if tail is None:
+        if len(_TAILS) > 65536:
+            _TAILS.clear()
+        tail = _TAILS[ck] = _ld(3, ck[0].encode()) + _key(4, 0) + _varint(ck[1])
+    return b"\x0a" + _varint(len(label)) + label + b"\x15" + struct.pack("<f", float(o["score"])) + tail
 
 
 def serialize_objects(objects: List[dict]) -> bytes:

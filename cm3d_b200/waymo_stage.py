@@ -230,7 +230,7 @@ def nms_objects(objects: List[dict]) -> List[dict]:
         by_ts.setdefault(o["frame_timestamp_micros"], []).append(o)
     final = []
     for ts, objs in by_ts.items():
-        dets = np.array([np.array([o["center_x"], o["center_y"], o["score"]]) for o in objs])
+        dets = np.array([[o["center_x"], o["center_y"], o["score"]] for o in objs], dtype=np.float64).reshape(-1, 3)
         keep = set(int(k) for k in B.circle_nms(dets, [o["type"] for o in objs], WAYMO_THRESHS))
         final.extend(o for c, o in enumerate(objs) if c in keep)
     return final
