@@ -51,23 +51,27 @@ _BOX_KEYS = tuple((n << 3) | 1 for _, n in _BOX_FIELDS)
 _TAILS = {}                                                   # per (context_name, timestamp) / per id: the constant bytes
 
 
+_F32 = struct.Struct("<f")
+_HEADS = {}                                                   # per (type, id): the bytes before and after the box
+
+
 def encode_object(o: dict) -> bytes:
     """One `Object` (field order and presence as `SerializeToString` of the proto2 message with every field set)."""
     k = _BOX_KEYS
     box = _BOX.pack(k[0], float(o["center_x"]), k[1], float(o["center_y"]), k[2], float(o["center_z"]), k[3], float(o["width"]),
                     k[4], float(o["length"]), k[5], float(o["height"]), k[6], float(o["heading"]))
-    oid = o.get("id", "unique object tracking ID")
-    id_part = _TAILS.get(oid)
-    if id_part is None:
-        id_part = _TAILS[oid] = _ld(4, oid.encode())
-    label = b"\x0a" + _varint(len(box)) + box + b"\x18" + _varint(int(o["type"])) + id_part
+    hk = (int(o["type"]), o.get("id", "unique object tracking ID"))
+    head = _HEADS.get(hk)
+    if head is None:                        # Object.object = Label { box = 1 (63 bytes), type = 3, id = 4 }
+        after = b"\x18" + _varint(hk[0]) + _ld(4, hk[1].encode())
+        head = _HEADS[hk] = (b"\x0a" + _varint(2 + _BOX.size + len(after)) + b"\x0a" + _varint(_BOX.size), after)
     ck = (o["context_name"], int(o["frame_timestamp_micros"]))
     tail = _TAILS.get(ck)
     if tail is None:
         if len(_TAILS) > 65536:
             _TAILS.clear()
         tail = _TAILS[ck] = _ld(3, ck[0].encode()) + _key(4, 0) + _varint(ck[1])
-    return b"\x0a" + _varint(len(label)) + label + b"\x15" + struct.pack("<f", float(o["score"])) + tail
+    return head[0] + box + head[1] + b"\x15" + _F32.pack(float(o["score"])) + tail
 
 
 def serialize_objects(objects: List[dict]) -> bytes:
