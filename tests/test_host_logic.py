@@ -453,3 +453,34 @@ def test_prefetch_map_keeps_order_bounds_lookahead_and_raises_in_place():
     assert got == [k * k for k in range(25)]
     assert list(prefetch_map(lambda k: k + 1, range(5), workers=1)) == [1, 2, 3, 4, 5]
     assert list(prefetch_map(lambda k: threading.get_ident(), range(3), workers=1)) == [threading.get_ident()] * 3
+
+
+def test_native_packer_column_selection_every_stride_and_tail():
+    """The C packer's column selection (whole-vector loads + shuffles, four rows at a time) against plain slicing
+    for 5-, 4- and 3-column sweeps of 0..13 rows, with and without the 4th column, including values whose bit
+    patterns a float copy must not touch (NaN payloads, -0.0, denormals)."""
+    import dataclasses
+    from cm3d_b200 import batch as B
+    from cm3d_b200 import synthetic as S
+    from cm3d_b200.synthetic import compress_rles, dense_to_rle
+    rng = np.random.default_rng(3)
+    base = {5: S.make_frame("c2", 1, scale=0.05, mask_div=2), 4: S.make_frame("c3", 2, scale=0.1, mask_div=2),
+            3: S.make_frame("c4", 3, scale=0.05, mask_div=2)}
+    for cols, f in base.items():
+        if isinstance(f.masks, np.ndarray):
+            f.masks = compress_rles(dense_to_rle(f.masks))
+        elif not all(isinstance(m.counts, (bytes, str)) for m in f.masks):
+            f.masks = compress_rles(f.masks)
+        assert f.sweeps[0].shape[1] == cols
+        for n in range(14):
+            bits = rng.integers(0, 2 ** 32, (n, cols), dtype=np.uint64).astype(np.uint32)
+            if n > 2:
+                bits[1, 0], bits[2, 1], bits[0, 2] = 0x7FC12345, 0x80000000, 0x00000001
+            sweep = bits.view(np.float32)
+            g = dataclasses.replace(f, sweeps=[sweep] + [np.zeros((0, cols), np.float32)] * (len(f.sweeps) - 1))
+            for keep in (True, False):
+                pb = B.pack_frames_native([g], keep_fourth=keep)
+                stride = 4 if (keep and g.fourth == 1 and cols >= 4) else 3
+                got = pb.raw.view(np.uint32)[:n * stride].reshape(n, stride)
+                assert np.array_equal(got, bits[:, :stride]), (cols, n, keep)
+                assert not pb.raw.view(np.uint32)[n * stride:(n * stride + 3) // 4 * 4].any()      # zero padding to 16 bytes
